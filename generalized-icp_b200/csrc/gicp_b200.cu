@@ -1,0 +1,755 @@
+// libgicp_b200.so - host side of the C ABI declared in include/gicp_b200.h.
+// Orchestrates the kernels K1 (grid.cuh), K2 (knn_cov.cuh), K3 (objective.cuh), K4 (solve.cuh).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gicp_b200.h"
+#include "grid.cuh"
+#include "knn_cov.cuh"
+#include "objective.cuh"
+#include "solve.cuh"
+
+using namespace gicp;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return 1;
+}
+
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return fail("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Grid {
+    DevBuf meta, cell_start, spts, inv_perm, bbox;
+    long long budget = 0;
+    long long total_cells = 0;
+    double h_target = 0;
+    bool built = false;
+    void release() { meta.release(); cell_start.release(); spts.release(); inv_perm.release(); bbox.release(); }
+};
+
+struct CloudSet {
+    const void* raw = nullptr;
+    std::vector<int64_t> offsets;
+    int n_clouds = 0;
+    int64_t n_total = 0;
+    int max_n = 0;
+    DevBuf d_offsets;   // int32 [n_clouds+1]
+    Grid knn;           // grid used for the covariance neighbourhoods (and source ordering)
+    Grid nn;            // target only: grid of the correspondence search (may be unused -> knn)
+    bool nn_separate = false;
+    DevBuf cov_knn;     // covariances in knn-grid order
+    DevBuf cov_nn;      // covariances in nn-grid order (target, when nn_separate)
+    bool ready = false;
+    void release() { d_offsets.release(); knn.release(); nn.release(); cov_knn.release(); cov_nn.release(); }
+};
+
+// NCCL through dlopen: the engine must load without NCCL when no communicator is requested.
+struct Id128 { char b[128]; };  // ncclUniqueId is 128 opaque bytes, passed by value
+typedef int (*nccl_init_fn)(void**, int, Id128, int);
+struct Nccl {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    nccl_init_fn CommInitRank = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+Nccl g_nccl;
+
+int load_nccl() {
+    if (g_nccl.lib) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return fail("cannot dlopen libnccl.so.2: %s", dlerror());
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (nccl_init_fn)dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllGather");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.AllGather || !g_nccl.CommDestroy)
+        return fail("libnccl is missing a required symbol");
+    return 0;
+}
+constexpr int NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_INT8 = 0;
+
+}  // namespace
+
+struct gicpContext {
+    int device = 0, dim = 2, storage = GICP_STORAGE_F64;
+    gicpParams prm;
+    CloudSet src, tgt;
+    DevBuf keys, keys_alt, vals, vals_alt, cub_tmp, cell_count, bbox_part, knn_idx_tmp;
+    DevBuf state, partial, red, T_dev, n_active;
+    int* h_poll = nullptr;  // pinned
+    cudaEvent_t poll_event = nullptr;
+    int64_t launches = 0;
+    // sharded-source mode
+    void* comm = nullptr;
+    int n_ranks = 1, rank = 0;
+};
+
+namespace {
+
+size_t real_size(const gicpContext* h) { return h->storage == GICP_STORAGE_F32 ? 4 : 8; }
+size_t prec_size(const gicpContext* h) { return h->storage == GICP_STORAGE_F32 ? 16 : 32; }
+int ns_of(int dim) { return dim * (dim + 1) / 2; }
+int nred_of(int dim) { return dim == 3 ? GICP_NRED_3D : GICP_NRED_2D; }
+
+template <int D, typename Real>
+int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, bool want_inv_perm, cudaStream_t st) {
+    const int nc = cs.n_clouds;
+    const int64_t n = cs.n_total;
+    long long budget = h->prm.max_cells_per_cloud;
+    if (budget <= 0) {
+        budget = 4LL * cs.max_n;
+        if (budget < 4096) budget = 4096;
+    }
+    if (budget * (long long)nc > (1LL << 30)) {
+        budget = (1LL << 30) / nc;
+        if (budget < 64) return fail("too many clouds for the cell table (%d)", nc);
+    }
+    g.budget = budget;
+    g.total_cells = budget * nc;
+    g.h_target = h_target;
+    const int chunks = std::max(1, (cs.max_n + BBOX_THREADS * BBOX_ITEMS - 1) / (BBOX_THREADS * BBOX_ITEMS));
+    CU(h->bbox_part.ensure((size_t)nc * chunks * 6 * sizeof(double)));
+    CU(g.meta.ensure((size_t)nc * sizeof(CloudMeta)));
+    CU(g.bbox.ensure((size_t)nc * 6 * sizeof(double)));
+    CU(g.cell_start.ensure((size_t)(g.total_cells + 1) * sizeof(int)));
+    CU(h->cell_count.ensure((size_t)(g.total_cells + 1) * sizeof(int)));
+    CU(g.spts.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(PRec<Real>)));
+    if (want_inv_perm) CU(g.inv_perm.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(int)));
+    CU(h->keys.ensure((size_t)std::max<int64_t>(n, 1) * 4));
+    CU(h->keys_alt.ensure((size_t)std::max<int64_t>(n, 1) * 4));
+    CU(h->vals.ensure((size_t)std::max<int64_t>(n, 1) * 4));
+    CU(h->vals_alt.ensure((size_t)std::max<int64_t>(n, 1) * 4));
+    const Real* pts = static_cast<const Real*>(cs.raw);
+    const int* offs = cs.d_offsets.as<int>();
+
+    bbox_partial_kernel<D, Real><<<dim3(chunks, nc), BBOX_THREADS, 0, st>>>(pts, offs, h->bbox_part.as<double>(), chunks);
+    grid_meta_kernel<D><<<(nc + 127) / 128, 128, 0, st>>>(h->bbox_part.as<double>(), chunks, offs, nc, h_target, budget,
+                                                          g.meta.as<CloudMeta>(), g.bbox.as<double>());
+    CU(cudaMemsetAsync(h->cell_count.p, 0, (size_t)(g.total_cells + 1) * sizeof(int), st));
+    h->launches += 2;
+    if (n > 0) {
+        const int bx = (cs.max_n + 255) / 256;
+        cell_key_kernel<D, Real><<<dim3(bx, nc), 256, 0, st>>>(pts, g.meta.as<CloudMeta>(), h->keys.as<unsigned>(),
+                                                               h->vals.as<int>(), h->cell_count.as<int>());
+        h->launches += 1;
+    }
+    {   // cell_start = exclusive scan of the histogram
+        size_t tmp = 0;
+        CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, h->cell_count.as<int>(), g.cell_start.as<int>(),
+                                         (int)(g.total_cells + 1), st));
+        CU(h->cub_tmp.ensure(tmp));
+        CU(cub::DeviceScan::ExclusiveSum(h->cub_tmp.p, tmp, h->cell_count.as<int>(), g.cell_start.as<int>(),
+                                         (int)(g.total_cells + 1), st));
+        h->launches += 2;
+    }
+    if (n > 0) {
+        int bits = 1;
+        while ((1LL << bits) < g.total_cells) ++bits;
+        cub::DoubleBuffer<unsigned> dk(h->keys.as<unsigned>(), h->keys_alt.as<unsigned>());
+        cub::DoubleBuffer<int> dv(h->vals.as<int>(), h->vals_alt.as<int>());
+        size_t tmp = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)n, 0, bits, st));
+        CU(h->cub_tmp.ensure(tmp));
+        CU(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp, dk, dv, (int)n, 0, bits, st));
+        h->launches += (bits + 7) / 8 + 2;
+        const int bx = (cs.max_n + 255) / 256;
+        gather_sorted_kernel<D, Real><<<dim3(bx, nc), 256, 0, st>>>(pts, g.meta.as<CloudMeta>(), dv.Current(),
+                                                                    g.spts.as<PRec<Real>>(),
+                                                                    want_inv_perm ? g.inv_perm.as<int>() : nullptr);
+        h->launches += 1;
+    }
+    CU(cudaGetLastError());
+    g.built = true;
+    return 0;
+}
+
+template <int D, typename Real>
+__global__ void regather_cov_kernel(const CloudMeta* __restrict__ meta, const PRec<Real>* __restrict__ spts_dst,
+                                    const int* __restrict__ inv_perm_src, const Real* __restrict__ cov_src,
+                                    Real* __restrict__ cov_dst) {
+    constexpr int NS = Dim<D>::NS;
+    const CloudMeta m = meta[blockIdx.y];
+    const int s = m.pt_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= m.pt_end) return;
+    const int g = m.pt_begin + (int)spts_dst[s].idx;
+    const int ss = inv_perm_src[g];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) cov_dst[(size_t)s * NS + i] = cov_src[(size_t)ss * NS + i];
+}
+
+template <int D, typename Real>
+__global__ void export_cov_kernel(const CloudMeta* __restrict__ meta, const PRec<Real>* __restrict__ spts,
+                                  const Real* __restrict__ cov_sorted, double* __restrict__ out) {
+    constexpr int NS = Dim<D>::NS;
+    const CloudMeta m = meta[blockIdx.y];
+    const int s = m.pt_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= m.pt_end) return;
+    const size_t g = (size_t)m.pt_begin + (size_t)spts[s].idx;
+    for (int i = 0; i < D; ++i)
+        for (int j = 0; j < D; ++j) out[g * D * D + i * D + j] = (double)cov_sorted[(size_t)s * NS + symidx(D, i, j)];
+}
+
+// out[t][g] = R_t C[g] R_t^T in input order (gicp.py:120-121)
+template <int D, typename Real>
+__global__ void rotated_cov_kernel(const CloudMeta* __restrict__ meta, const PRec<Real>* __restrict__ spts,
+                                   const Real* __restrict__ cov_sorted, const double* __restrict__ T, int n_clouds,
+                                   size_t n_total, double* __restrict__ out) {
+    constexpr int NS = Dim<D>::NS;
+    const CloudMeta m = meta[blockIdx.y];
+    const int s = m.pt_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= m.pt_end) return;
+    const int t = blockIdx.z;
+    const double* Tm = T + ((size_t)t * n_clouds + blockIdx.y) * (D + 1) * (D + 1);
+    double C[D][D], A[D][D];
+    for (int i = 0; i < D; ++i)
+        for (int j = 0; j < D; ++j) C[i][j] = (double)cov_sorted[(size_t)s * NS + symidx(D, i, j)];
+    for (int i = 0; i < D; ++i)
+        for (int j = 0; j < D; ++j) {
+            double v = 0.0;
+            for (int k = 0; k < D; ++k) v += Tm[i * (D + 1) + k] * C[k][j];
+            A[i][j] = v;
+        }
+    const size_t g = (size_t)m.pt_begin + (size_t)spts[s].idx;
+    double* o = out + ((size_t)t * n_total + g) * D * D;
+    for (int i = 0; i < D; ++i)
+        for (int j = 0; j < D; ++j) {
+            double v = 0.0;
+            for (int k = 0; k < D; ++k) v += A[i][k] * Tm[j * (D + 1) + k];
+            o[i * D + j] = v;
+        }
+}
+
+template <int D, typename Real>
+int launch_knn(gicpContext* h, CloudSet& cs, int* d_idx, double* d_dist, cudaStream_t st, int slice_b, int slice_e) {
+    KnnArgs<Real> a;
+    a.meta = cs.knn.meta.as<CloudMeta>();
+    a.cell_start = cs.knn.cell_start.as<int>();
+    a.spts = cs.knn.spts.as<PRec<Real>>();
+    a.raw = static_cast<const Real*>(cs.raw);
+    a.cov_sorted = cs.cov_knn.as<Real>();
+    a.knn_idx = d_idx;
+    a.knn_dist = d_dist;
+    a.k = h->prm.k;
+    a.radius = h->prm.max_distance_nearest_neighbors;
+    a.lam_t = h->prm.lambda_tangent;
+    a.lam_n = h->prm.lambda_normal;
+    a.slice_begin = slice_b;
+    a.slice_end = slice_e;
+    if (cs.n_total == 0) return 0;
+    const int span = (slice_b >= 0) ? (slice_e - slice_b) : cs.max_n;
+    if (span <= 0) return 0;
+    const int bx = (span + KNN_THREADS - 1) / KNN_THREADS;
+    const size_t smem = 128 + (size_t)KNN_WARPS * KNN_STAGE_BYTES;
+    dim3 grid(bx, cs.n_clouds);
+#define KNN_LAUNCH(KC)                                                                                       \
+    do {                                                                                                     \
+        CU(cudaFuncSetAttribute(knn_cov_kernel<D, Real, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                (int)smem));                                                                 \
+        knn_cov_kernel<D, Real, KC><<<grid, KNN_THREADS, smem, st>>>(a);                                     \
+    } while (0)
+    if (a.k <= 6) KNN_LAUNCH(6);
+    else if (a.k <= 20) KNN_LAUNCH(20);
+    else KNN_LAUNCH(32);
+#undef KNN_LAUNCH
+    h->launches += 1;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+double auto_knn_cell(const gicpContext* h) {
+    if (h->prm.knn_cell > 0) return h->prm.knn_cell;
+    return 0.5 * h->prm.max_distance_nearest_neighbors * (1.0 + 1e-6);
+}
+double auto_nn_cell(const gicpContext* h) {
+    if (h->prm.nn_cell > 0) return h->prm.nn_cell;
+    return 0.5 * h->prm.max_distance_correspondence * (1.0 + 1e-6);
+}
+
+template <int D, typename Real>
+int set_cloud(gicpContext* h, int which, const void* d_points, const int64_t* h_offsets, int n_clouds,
+              cudaStream_t st) {
+    CloudSet& cs = which == GICP_TARGET ? h->tgt : h->src;
+    cs.ready = false;
+    if (n_clouds <= 0) return fail("n_clouds must be positive");
+    if (n_clouds > 65535) return fail("at most 65535 clouds per batch (got %d)", n_clouds);
+    cs.raw = d_points;
+    cs.n_clouds = n_clouds;
+    cs.offsets.assign(h_offsets, h_offsets + n_clouds + 1);
+    cs.n_total = h_offsets[n_clouds] - h_offsets[0];
+    if (h_offsets[0] != 0) return fail("offsets[0] must be 0");
+    if (cs.n_total >= (1LL << 31) - 1024) return fail("more than 2^31 points in one batch");
+    cs.max_n = 0;
+    std::vector<int> off32(n_clouds + 1);
+    for (int i = 0; i <= n_clouds; ++i) {
+        off32[i] = (int)h_offsets[i];
+        if (i && h_offsets[i] < h_offsets[i - 1]) return fail("offsets must be non-decreasing");
+        if (i) cs.max_n = std::max<int>(cs.max_n, (int)(h_offsets[i] - h_offsets[i - 1]));
+    }
+    if (cs.n_total > 0 && !d_points) return fail("null point array");
+    CU(cs.d_offsets.ensure(off32.size() * sizeof(int)));
+    CU(cudaMemcpyAsync(cs.d_offsets.p, off32.data(), off32.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));  // off32 is a stack-lifetime staging buffer
+
+    const double h_knn = auto_knn_cell(h);
+    const double h_nn = auto_nn_cell(h);
+    cs.nn_separate = (which == GICP_TARGET) && (fabs(h_nn - h_knn) > 0.2 * h_knn);
+    if (build_grid<D, Real>(h, cs, cs.knn, h_knn, cs.nn_separate, st)) return 1;
+    CU(cs.cov_knn.ensure((size_t)std::max<int64_t>(cs.n_total, 1) * ns_of(D) * sizeof(Real)));
+
+    // covariances; in sharded mode the target slice is computed locally and all-gathered
+    int slice_b = -1, slice_e = -1;
+    if (h->comm && n_clouds == 1) {
+        const int64_t n = cs.n_total;
+        slice_b = (int)(n * h->rank / h->n_ranks);
+        slice_e = (int)(n * (h->rank + 1) / h->n_ranks);
+        if (which == GICP_TARGET) {
+            // equal-sized slices are required by ncclAllGather: round the slice length up
+            const int64_t per = (n + h->n_ranks - 1) / h->n_ranks;
+            slice_b = (int)std::min<int64_t>(n, per * h->rank);
+            slice_e = (int)std::min<int64_t>(n, per * (h->rank + 1));
+            CU(cs.cov_knn.ensure((size_t)per * h->n_ranks * ns_of(D) * sizeof(Real)));
+        }
+    }
+    if (launch_knn<D, Real>(h, cs, nullptr, nullptr, st, slice_b, slice_e)) return 1;
+    if (h->comm && n_clouds == 1 && which == GICP_TARGET) {
+        const int64_t per = (cs.n_total + h->n_ranks - 1) / h->n_ranks;
+        const size_t bytes = (size_t)per * ns_of(D) * sizeof(Real);
+        char* basep = cs.cov_knn.as<char>();
+        int rc = g_nccl.AllGather(basep + bytes * h->rank, basep, bytes, NCCL_INT8, h->comm, st);
+        if (rc) return fail("ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    }
+    if (cs.nn_separate) {
+        if (build_grid<D, Real>(h, cs, cs.nn, h_nn, false, st)) return 1;
+        CU(cs.cov_nn.ensure((size_t)std::max<int64_t>(cs.n_total, 1) * ns_of(D) * sizeof(Real)));
+        if (cs.n_total > 0) {
+            const int bx = (cs.max_n + 255) / 256;
+            regather_cov_kernel<D, Real><<<dim3(bx, n_clouds), 256, 0, st>>>(
+                cs.nn.meta.as<CloudMeta>(), cs.nn.spts.as<PRec<Real>>(), cs.knn.inv_perm.as<int>(),
+                cs.cov_knn.as<Real>(), cs.cov_nn.as<Real>());
+            h->launches += 1;
+        }
+    }
+    CU(cudaGetLastError());
+    cs.ready = true;
+    return 0;
+}
+
+template <int D, typename Real>
+int objective_args(gicpContext* h, ObjArgs<Real>& a, int& blocks_per_pair, bool allow_slice) {
+    CloudSet &S = h->src, &T = h->tgt;
+    if (!S.ready || !T.ready) return fail("set source and target first");
+    if (S.n_clouds != T.n_clouds) return fail("source has %d clouds, target %d", S.n_clouds, T.n_clouds);
+    const Grid& tg = T.nn_separate ? T.nn : T.knn;
+    a.src_meta = S.knn.meta.as<CloudMeta>();
+    a.src_spts = S.knn.spts.as<PRec<Real>>();
+    a.src_cov = S.cov_knn.as<Real>();
+    a.tgt_meta = tg.meta.as<CloudMeta>();
+    a.tgt_cell_start = tg.cell_start.as<int>();
+    a.tgt_spts = tg.spts.as<PRec<Real>>();
+    a.tgt_cov = T.nn_separate ? T.cov_nn.as<Real>() : T.cov_knn.as<Real>();
+    CU(h->state.ensure((size_t)S.n_clouds * sizeof(PairState)));
+    a.state = h->state.as<PairState>();
+    a.T_override = nullptr;
+    a.d_max = h->prm.max_distance_correspondence;
+    a.out_idx = nullptr;
+    a.out_dist = nullptr;
+    a.out_W = nullptr;
+    a.slice_begin = a.slice_end = -1;
+    a.ignore_status = 0;
+    int span = S.max_n;
+    if (allow_slice && h->comm && S.n_clouds == 1) {
+        a.slice_begin = (int)(S.n_total * h->rank / h->n_ranks);
+        a.slice_end = (int)(S.n_total * (h->rank + 1) / h->n_ranks);
+        span = a.slice_end - a.slice_begin;
+    }
+    // enough blocks to fill the machine, as many points per thread as that allows (<= 16)
+    const long long total_pts = (long long)std::max(span, 1) * S.n_clouds;
+    int ppt = (int)(total_pts / (148LL * 8 * OBJ_THREADS));
+    ppt = std::max(1, std::min(16, ppt));
+    a.ppt = ppt;
+    blocks_per_pair = std::max(1, (span + OBJ_THREADS * ppt - 1) / (OBJ_THREADS * ppt));
+    a.blocks_per_pair = blocks_per_pair;
+    CU(h->partial.ensure((size_t)S.n_clouds * blocks_per_pair * Dim<D>::NRED * sizeof(double)));
+    CU(h->red.ensure((size_t)S.n_clouds * Dim<D>::NRED * sizeof(double)));
+    a.partial = h->partial.as<double>();
+    return 0;
+}
+
+template <int D, typename Real>
+int ensure_state(gicpContext* h, const double* h_T0, double* d_T, double* d_T_hist, int* d_n_outer,
+                 int* d_converged, cudaStream_t st) {
+    const int np = h->src.n_clouds;
+    CU(h->state.ensure((size_t)np * sizeof(PairState)));
+    CU(h->n_active.ensure(sizeof(int)));
+    const double* d_T0 = nullptr;
+    if (h_T0) {
+        const size_t bytes = (size_t)np * (D + 1) * (D + 1) * sizeof(double);
+        CU(h->T_dev.ensure(bytes));
+        CU(cudaMemcpyAsync(h->T_dev.p, h_T0, bytes, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+        d_T0 = h->T_dev.as<double>();
+    }
+    init_state_kernel<D><<<(np + 127) / 128, 128, 0, st>>>(h->state.as<PairState>(), d_T0, h->tgt.knn.bbox.as<double>(), np,
+                                                           d_T, d_T_hist, h->prm.max_iterations, d_n_outer, d_converged);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <int D, typename Real>
+int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer, int* d_converged,
+                double* d_loss_hist, double* d_T_hist, int* d_inliers, cudaStream_t st) {
+    ObjArgs<Real> oa;
+    int bpp = 1;
+    if (objective_args<D, Real>(h, oa, bpp, true)) return 1;
+    const int np = h->src.n_clouds;
+    if (ensure_state<D, Real>(h, h_T0, d_T, d_T_hist, d_n_outer, d_converged, st)) return 1;
+    CU(cudaMemcpyAsync(h->n_active.p, &np, sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    SolveArgs sa;
+    sa.partial = h->partial.as<double>();
+    sa.blocks_per_pair = bpp;
+    sa.n_pairs = np;
+    sa.sum_out = nullptr;
+    sa.state = h->state.as<PairState>();
+    sa.max_iterations = h->prm.max_iterations;
+    sa.inner_max_iterations = h->prm.inner_max_iterations;
+    sa.tolerance = h->prm.tolerance;
+    sa.d_T = d_T;
+    sa.d_n_outer = d_n_outer;
+    sa.d_converged = d_converged;
+    sa.d_loss_hist = d_loss_hist;
+    sa.d_T_hist = d_T_hist;
+    sa.d_inliers = d_inliers;
+    sa.n_active = h->n_active.as<int>();
+    const dim3 ogrid(bpp, np);
+    const int sgrid = (np + SOLVE_WARPS - 1) / SOLVE_WARPS;
+    const bool sharded = h->comm && np == 1;
+    *h->h_poll = np;
+    const int poll_every = 2;
+    for (int it = 0; it < h->prm.max_iterations; ++it) {
+        objective_kernel<D, Real><<<ogrid, OBJ_THREADS, 0, st>>>(oa);
+        if (sharded) {
+            SolveArgs s1 = sa;
+            s1.sum_out = h->red.as<double>();
+            solve_kernel<D><<<sgrid, SOLVE_WARPS * 32, 0, st>>>(s1);
+            int rc = g_nccl.AllReduce(h->red.p, h->red.p, (size_t)Dim<D>::NRED, NCCL_FLOAT64, NCCL_SUM, h->comm, st);
+            if (rc) return fail("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+            SolveArgs s2 = sa;
+            s2.partial = h->red.as<double>();
+            s2.blocks_per_pair = 1;
+            solve_kernel<D><<<sgrid, SOLVE_WARPS * 32, 0, st>>>(s2);
+            h->launches += 3;
+        } else {
+            solve_kernel<D><<<sgrid, SOLVE_WARPS * 32, 0, st>>>(sa);
+            h->launches += 2;
+        }
+        if ((it + 1) % poll_every == 0 || it + 1 == h->prm.max_iterations) {
+            // progress poll: 4 bytes, the only host<->device traffic inside the loop
+            CU(cudaMemcpyAsync(h->h_poll, h->n_active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (*h->h_poll <= 0) break;
+        }
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <int D, typename Real>
+int do_stage(gicpContext* h, const double* h_T, int* d_idx, double* d_dist, double* d_W, double* h_out,
+             cudaStream_t st) {
+    ObjArgs<Real> oa;
+    int bpp = 1;
+    if (objective_args<D, Real>(h, oa, bpp, false)) return 1;
+    const int np = h->src.n_clouds;
+    if (!h_T) return fail("h_T is required");
+    if (ensure_state<D, Real>(h, nullptr, nullptr, nullptr, nullptr, nullptr, st)) return 1;
+    const size_t bytes = (size_t)np * (D + 1) * (D + 1) * sizeof(double);
+    CU(h->T_dev.ensure(bytes));
+    CU(cudaMemcpyAsync(h->T_dev.p, h_T, bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    oa.T_override = h->T_dev.as<double>();
+    oa.out_idx = d_idx;
+    oa.out_dist = d_dist;
+    oa.out_W = d_W;
+    oa.ignore_status = 1;
+    // stage entry points always cover the whole source (no slicing), so their outputs are complete
+    objective_kernel<D, Real><<<dim3(bpp, np), OBJ_THREADS, 0, st>>>(oa);
+    h->launches += 1;
+    if (h_out) {
+        SolveArgs sa;
+        memset(&sa, 0, sizeof sa);
+        sa.partial = h->partial.as<double>();
+        sa.blocks_per_pair = bpp;
+        sa.n_pairs = np;
+        sa.sum_out = h->red.as<double>();
+        sa.state = h->state.as<PairState>();
+        solve_kernel<D><<<(np + SOLVE_WARPS - 1) / SOLVE_WARPS, SOLVE_WARPS * 32, 0, st>>>(sa);
+        h->launches += 1;
+        CU(cudaMemcpyAsync(h_out, h->red.p, (size_t)np * Dim<D>::NRED * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <int D, typename Real>
+int do_knn(gicpContext* h, int which, int* d_idx, double* d_dist, cudaStream_t st) {
+    CloudSet& cs = which == GICP_TARGET ? h->tgt : h->src;
+    if (!cs.ready) return fail("cloud not set");
+    // re-runs K2 with the index outputs enabled (covariances are rewritten with identical values)
+    return launch_knn<D, Real>(h, cs, d_idx, d_dist, st, -1, -1);
+}
+
+template <int D, typename Real>
+int do_cov(gicpContext* h, int which, double* d_cov, cudaStream_t st) {
+    CloudSet& cs = which == GICP_TARGET ? h->tgt : h->src;
+    if (!cs.ready) return fail("cloud not set");
+    if (cs.n_total == 0) return 0;
+    const int bx = (cs.max_n + 255) / 256;
+    export_cov_kernel<D, Real><<<dim3(bx, cs.n_clouds), 256, 0, st>>>(cs.knn.meta.as<CloudMeta>(),
+                                                                      cs.knn.spts.as<PRec<Real>>(),
+                                                                      cs.cov_knn.as<Real>(), d_cov);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <int D, typename Real>
+int do_rotcov(gicpContext* h, const double* h_T, int n_T, double* d_out, cudaStream_t st) {
+    CloudSet& cs = h->src;
+    if (!cs.ready) return fail("source not set");
+    if (n_T <= 0 || cs.n_total == 0) return 0;
+    if (n_T > 65535) return fail("n_T too large");
+    const size_t bytes = (size_t)n_T * cs.n_clouds * (D + 1) * (D + 1) * sizeof(double);
+    CU(h->T_dev.ensure(bytes));
+    CU(cudaMemcpyAsync(h->T_dev.p, h_T, bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    const int bx = (cs.max_n + 255) / 256;
+    rotated_cov_kernel<D, Real><<<dim3(bx, cs.n_clouds, n_T), 256, 0, st>>>(
+        cs.knn.meta.as<CloudMeta>(), cs.knn.spts.as<PRec<Real>>(), cs.cov_knn.as<Real>(), h->T_dev.as<double>(),
+        cs.n_clouds, (size_t)cs.n_total, d_out);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+#define DISPATCH(h, FN, ...)                                                                  \
+    ((h)->dim == 2 ? ((h)->storage == GICP_STORAGE_F32 ? FN<2, float>(__VA_ARGS__) : FN<2, double>(__VA_ARGS__)) \
+                   : ((h)->storage == GICP_STORAGE_F32 ? FN<3, float>(__VA_ARGS__) : FN<3, double>(__VA_ARGS__)))
+
+int check(gicpHandle h) {
+    if (!h) return fail("null handle");
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return fail("cudaSetDevice(%d): %s", h->device, cudaGetErrorString(e));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gicpGetLastError(void) { return g_last_error.c_str(); }
+int gicpVersion(void) { return 100; }
+
+int gicpDefaultParams(gicpParams* p) {
+    if (!p) return fail("null params");
+    memset(p, 0, sizeof *p);
+    p->k = 6;
+    p->max_iterations = 100;
+    p->tolerance = 1e-6;
+    p->max_distance_correspondence = 150.0;
+    p->max_distance_nearest_neighbors = 50.0;
+    p->lambda_tangent = 100.0;
+    p->lambda_normal = 10.0;
+    p->inner_max_iterations = 50;
+    return 0;
+}
+
+int gicpCreate(gicpHandle* out, int device, int dim, int storage) {
+    if (!out) return fail("null out");
+    if (dim != 2 && dim != 3) return fail("dim must be 2 or 3 (got %d)", dim);
+    if (storage != GICP_STORAGE_F32 && storage != GICP_STORAGE_F64) return fail("bad storage %d", storage);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail("no CUDA device available (%s): this engine has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail("device %d out of range (%d devices)", device, count);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 9) return fail("device %d is sm_%d%d; this library is built for sm_100a", device, prop.major, prop.minor);
+    gicpContext* h = new gicpContext();
+    h->device = device;
+    h->dim = dim;
+    h->storage = storage;
+    gicpDefaultParams(&h->prm);
+    CU(cudaMallocHost(&h->h_poll, sizeof(int)));
+    *out = h;
+    return 0;
+}
+
+int gicpDestroy(gicpHandle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    h->src.release();
+    h->tgt.release();
+    DevBuf* bufs[] = {&h->keys, &h->keys_alt, &h->vals, &h->vals_alt, &h->cub_tmp, &h->cell_count, &h->bbox_part,
+                      &h->knn_idx_tmp, &h->state, &h->partial, &h->red, &h->T_dev, &h->n_active};
+    for (DevBuf* b : bufs) b->release();
+    if (h->h_poll) cudaFreeHost(h->h_poll);
+    delete h;
+    return 0;
+}
+
+int gicpSetParams(gicpHandle h, const gicpParams* p) {
+    if (check(h)) return 1;
+    if (!p) return fail("null params");
+    if (p->k < 1 || p->k > 32) return fail("k must be in [1, 32] (got %d)", p->k);
+    if (p->max_iterations < 1) return fail("max_iterations must be >= 1");
+    if (!(p->max_distance_nearest_neighbors > 0)) return fail("max_distance_nearest_neighbors must be > 0");
+    if (!(p->max_distance_correspondence > 0)) return fail("max_distance_correspondence must be > 0");
+    h->prm = *p;
+    if (h->prm.inner_max_iterations <= 0) h->prm.inner_max_iterations = 50;
+    h->src.ready = false;
+    h->tgt.ready = false;
+    return 0;
+}
+
+int gicpSetTarget(gicpHandle h, const void* d_points, const int64_t* h_offsets, int32_t n_clouds, void* stream) {
+    if (check(h)) return 1;
+    if (!h_offsets) return fail("null offsets");
+    return DISPATCH(h, set_cloud, h, GICP_TARGET, d_points, h_offsets, n_clouds, (cudaStream_t)stream);
+}
+
+int gicpSetSource(gicpHandle h, const void* d_points, const int64_t* h_offsets, int32_t n_clouds, void* stream) {
+    if (check(h)) return 1;
+    if (!h_offsets) return fail("null offsets");
+    return DISPATCH(h, set_cloud, h, GICP_SOURCE, d_points, h_offsets, n_clouds, (cudaStream_t)stream);
+}
+
+int gicpRegister(gicpHandle h, const double* h_T0, double* d_T, int32_t* d_n_outer, int32_t* d_converged,
+                 double* d_loss_hist, double* d_T_hist, int32_t* d_inliers, void* stream) {
+    if (check(h)) return 1;
+    if (!d_T || !d_n_outer || !d_converged) return fail("d_T, d_n_outer and d_converged are required");
+    return DISPATCH(h, do_register, h, h_T0, d_T, d_n_outer, d_converged, d_loss_hist, d_T_hist, d_inliers,
+                    (cudaStream_t)stream);
+}
+
+int gicpKnn(gicpHandle h, int which, int32_t* d_idx, double* d_dist, void* stream) {
+    if (check(h)) return 1;
+    if (!d_idx) return fail("d_idx is required");
+    return DISPATCH(h, do_knn, h, which, d_idx, d_dist, (cudaStream_t)stream);
+}
+
+int gicpCovariances(gicpHandle h, int which, double* d_cov, void* stream) {
+    if (check(h)) return 1;
+    if (!d_cov) return fail("d_cov is required");
+    return DISPATCH(h, do_cov, h, which, d_cov, (cudaStream_t)stream);
+}
+
+int gicpCorrespond(gicpHandle h, const double* h_T, int32_t* d_idx, double* d_dist, double* d_W, void* stream) {
+    if (check(h)) return 1;
+    return DISPATCH(h, do_stage, h, h_T, d_idx, d_dist, d_W, (double*)nullptr, (cudaStream_t)stream);
+}
+
+int gicpNormalEquations(gicpHandle h, const double* h_T, double* h_out, void* stream) {
+    if (check(h)) return 1;
+    if (!h_out) return fail("h_out is required");
+    return DISPATCH(h, do_stage, h, h_T, (int*)nullptr, (double*)nullptr, (double*)nullptr, h_out,
+                    (cudaStream_t)stream);
+}
+
+int gicpSourceCovariancesAt(gicpHandle h, const double* h_T, int32_t n_T, double* d_out, void* stream) {
+    if (check(h)) return 1;
+    if (!h_T || !d_out) return fail("h_T and d_out are required");
+    return DISPATCH(h, do_rotcov, h, h_T, n_T, d_out, (cudaStream_t)stream);
+}
+
+int gicpCommGetUniqueId(char id[128]) {
+    if (load_nccl()) return 1;
+    int rc = g_nccl.GetUniqueId(id);
+    if (rc) return fail("ncclGetUniqueId failed (%d)", rc);
+    return 0;
+}
+
+int gicpCommInit(gicpHandle h, int32_t n_ranks, int32_t rank, const char id[128]) {
+    if (check(h)) return 1;
+    if (load_nccl()) return 1;
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail("bad rank %d / %d", rank, n_ranks);
+    Id128 u;
+    memcpy(u.b, id, 128);
+    void* comm = nullptr;
+    int rc = g_nccl.CommInitRank(&comm, n_ranks, u, rank);
+    if (rc) return fail("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    h->comm = comm;
+    h->n_ranks = n_ranks;
+    h->rank = rank;
+    h->src.ready = h->tgt.ready = false;
+    return 0;
+}
+
+int gicpCommDestroy(gicpHandle h) {
+    if (check(h)) return 1;
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    h->comm = nullptr;
+    h->n_ranks = 1;
+    h->rank = 0;
+    return 0;
+}
+
+int64_t gicpLaunchCount(gicpHandle h) { return h ? h->launches : 0; }
+
+}  // extern "C"

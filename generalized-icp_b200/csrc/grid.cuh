@@ -1,0 +1,157 @@
+// K1: uniform-grid build.  Replaces scipy's KDTree(points) (reference gicp.py:21,127).
+//   bbox -> per-cloud grid geometry -> cell key per point (+ histogram) -> radix sort by key
+//   -> exclusive scan of the histogram = cell_start -> gather points into sorted records.
+#pragma once
+#include "common.cuh"
+
+namespace gicp {
+
+constexpr int BBOX_THREADS = 256;
+constexpr int BBOX_ITEMS = 16;  // points per thread
+
+// grid (chunks, n_clouds): per-chunk min/max of every coordinate -> part[cloud][chunk][2*3]
+template <int D, typename Real>
+__global__ void __launch_bounds__(BBOX_THREADS) bbox_partial_kernel(const Real* __restrict__ pts,
+                                                                    const int* __restrict__ offsets,
+                                                                    double* __restrict__ part, int chunks) {
+    const int cloud = blockIdx.y;
+    const int b = offsets[cloud], e = offsets[cloud + 1];
+    const int c0 = b + blockIdx.x * (BBOX_THREADS * BBOX_ITEMS);
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (c0 < e) {
+#pragma unroll 4
+        for (int i = 0; i < BBOX_ITEMS; ++i) {
+            const int g = c0 + i * BBOX_THREADS + threadIdx.x;
+            if (g < e) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    const double v = (double)pts[(size_t)g * D + c];
+                    if (isfinite(v)) { lo[c] = fmin(lo[c], v); hi[c] = fmax(hi[c], v); }
+                }
+            }
+        }
+    }
+    __shared__ double s_lo[BBOX_THREADS / 32][3], s_hi[BBOX_THREADS / 32][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fmin(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmax(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        for (int c = 0; c < 3; ++c) { s_lo[w][c] = lo[c]; s_hi[w][c] = hi[c]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int c = threadIdx.x;
+        double l = s_lo[0][c], h = s_hi[0][c];
+        for (int i = 1; i < BBOX_THREADS / 32; ++i) { l = fmin(l, s_lo[i][c]); h = fmax(h, s_hi[i][c]); }
+        double* o = part + ((size_t)cloud * chunks + blockIdx.x) * 6;
+        o[c] = l;
+        o[3 + c] = h;
+    }
+}
+
+// one thread per cloud: reduce the partial boxes, choose the cell edge, lay out the cell table.
+// bbox_out[cloud][6] keeps (lo, hi) for later use (centring point of the reduced form).
+template <int D>
+__global__ void grid_meta_kernel(const double* __restrict__ part, int chunks, const int* __restrict__ offsets,
+                                 int n_clouds, double h_target, long long budget, CloudMeta* __restrict__ meta,
+                                 double* __restrict__ bbox_out) {
+    const int cloud = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cloud >= n_clouds) return;
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    const int n = offsets[cloud + 1] - offsets[cloud];
+    const int used = min(chunks, (n + BBOX_THREADS * BBOX_ITEMS - 1) / (BBOX_THREADS * BBOX_ITEMS));
+    for (int k = 0; k < used; ++k) {
+        const double* p = part + ((size_t)cloud * chunks + k) * 6;
+        for (int c = 0; c < D; ++c) { lo[c] = fmin(lo[c], p[c]); hi[c] = fmax(hi[c], p[3 + c]); }
+    }
+    for (int c = 0; c < 3; ++c) {
+        if (c >= D || !(lo[c] <= hi[c])) { lo[c] = 0.0; hi[c] = 0.0; }
+    }
+    double h = h_target;
+    int dims[3];
+    for (int guard = 0; guard < 400; ++guard) {
+        long long total = 1;
+        for (int c = 0; c < 3; ++c) {
+            double d = floor((hi[c] - lo[c]) / h) + 1.0;
+            d = fmin(d, 2.0e9);
+            dims[c] = (c < D) ? (int)d : 1;
+            total = (total > (long long)4e18 / dims[c]) ? (long long)4e18 : total * dims[c];
+        }
+        if (total <= budget) break;
+        h *= 1.2599210498948732;  // doubles the cell volume in 3-D
+    }
+    CloudMeta m;
+    for (int c = 0; c < 3; ++c) { m.origin[c] = lo[c]; m.dims[c] = dims[c]; }
+    m.h = h;
+    m.inv_h = 1.0 / h;
+    m.cell_base = (int)((long long)cloud * budget);
+    m.pt_begin = offsets[cloud];
+    m.pt_end = offsets[cloud + 1];
+    // dims must reproduce what cell_coord() gives for the extreme points
+    for (int c = 0; c < D; ++c) m.dims[c] = cell_coord(hi[c], lo[c], m.inv_h) + 1;
+    {   // the recomputed dims can exceed the estimate by one cell through rounding: re-check
+        long long total = 1;
+        for (int c = 0; c < 3; ++c) total *= m.dims[c];
+        if (total > budget) {
+            m.h = h * 1.2599210498948732;
+            m.inv_h = 1.0 / m.h;
+            for (int c = 0; c < D; ++c) m.dims[c] = cell_coord(hi[c], lo[c], m.inv_h) + 1;
+        }
+    }
+    meta[cloud] = m;
+    if (bbox_out) {
+        for (int c = 0; c < 3; ++c) { bbox_out[cloud * 6 + c] = lo[c]; bbox_out[cloud * 6 + 3 + c] = hi[c]; }
+    }
+}
+
+// grid (blocks, n_clouds): cell key of every point, histogram of cell populations.
+template <int D, typename Real>
+__global__ void __launch_bounds__(256) cell_key_kernel(const Real* __restrict__ pts, const CloudMeta* __restrict__ meta,
+                                                       unsigned* __restrict__ keys, int* __restrict__ vals,
+                                                       int* __restrict__ cell_count) {
+    const CloudMeta m = meta[blockIdx.y];
+    const int g = m.pt_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= m.pt_end) return;
+    int c[3] = {0, 0, 0};
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+        const int v = cell_coord((double)pts[(size_t)g * D + a], m.origin[a], m.inv_h);
+        c[a] = min(max(v, 0), m.dims[a] - 1);
+    }
+    const int cell = m.cell_base + (c[2] * m.dims[1] + c[1]) * m.dims[0] + c[0];
+    keys[g] = (unsigned)cell;
+    vals[g] = g;
+    atomicAdd(&cell_count[cell], 1);
+}
+
+// grid (blocks, n_clouds): sorted position s -> record {coords, cloud-local index}; inverse permutation.
+template <int D, typename Real>
+__global__ void __launch_bounds__(256) gather_sorted_kernel(const Real* __restrict__ pts,
+                                                            const CloudMeta* __restrict__ meta,
+                                                            const int* __restrict__ sorted_vals,
+                                                            PRec<Real>* __restrict__ spts, int* __restrict__ inv_perm) {
+    const CloudMeta m = meta[blockIdx.y];
+    const int s = m.pt_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= m.pt_end) return;
+    const int g = sorted_vals[s];
+    PRec<Real> r;
+    r.x = pts[(size_t)g * D + 0];
+    r.y = pts[(size_t)g * D + 1];
+    r.z = (D == 3) ? pts[(size_t)g * D + (D - 1)] : Real(0);
+    r.idx = g - m.pt_begin;
+    spts[s] = r;
+    if (inv_perm) inv_perm[g] = s;
+}
+
+__global__ void offsets_to_int_kernel(const long long* __restrict__ in, int* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int)in[i];
+}
+
+}  // namespace gicp

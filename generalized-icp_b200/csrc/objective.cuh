@@ -1,0 +1,262 @@
+// K3: the fused per-iteration pass.  Replaces, per outer iteration of the reference loop,
+//   apply_transformation (gicp.py:119), the per-point 1-NN query + d_max gate (gicp.py:129-138),
+//   W_i = inv(C_src,k[i] + C_tgt[j]) (gicp.py:143-145; C_src,k = R_k C_src,0 R_k^T, which equals the
+//   reference's recomputation on the transformed cloud, gicp.py:120) and every loss / grad_loss
+//   evaluation of the inner minimisation (gicp.py:52-76): with W and the matches frozen, the
+//   residual  r_i = e_i - Z p~_i  (e_i = q_i - p'_i, p~_i = (1, p'_i - mu), Z = [dt | dR - I])  is
+//   linear in Z, so one streaming pass that reduces  sum p~p~^T (x) W,  sum (W e) p~^T  and
+//   sum e^T W e  gives the inner objective exactly; K4 then minimises it without touching the
+//   points again.
+//
+// One thread per source point (cell-sorted order, so a warp's queries hit neighbouring target
+// cells).  Exactness: an fp32 distance with a proven error margin filters candidates, the ranked
+// key is the float64 squared distance of the oracle, ties go to the lower target index.
+// Per-point algebra runs in fp64; products are accumulated per thread in the storage precision,
+// reduced with warp shuffles, then across warps and blocks in fp64 in a fixed order (bitwise
+// reproducible, no float atomics).
+#pragma once
+#include "common.cuh"
+
+namespace gicp {
+
+constexpr int OBJ_THREADS = 128;
+
+template <typename Real> struct ObjArgs {
+    const CloudMeta* src_meta;
+    const PRec<Real>* src_spts;
+    const Real* src_cov;
+    const CloudMeta* tgt_meta;
+    const int* tgt_cell_start;
+    const PRec<Real>* tgt_spts;
+    const Real* tgt_cov;
+    const PairState* state;
+    const double* T_override;  // optional [n_pairs][(D+1)^2], device
+    double* partial;           // [n_pairs][blocks_per_pair][NRED]
+    int blocks_per_pair;
+    int ppt;
+    double d_max;
+    int* out_idx;
+    double* out_dist;
+    double* out_W;
+    int slice_begin, slice_end;
+    int ignore_status;
+};
+
+template <int D, typename Real>
+__global__ void __launch_bounds__(OBJ_THREADS) objective_kernel(const ObjArgs<Real> a) {
+    using DD = Dim<D>;
+    using AccT = Real;
+    constexpr int NP = DD::NP, NS = DD::NS, NH = DD::NH, NQ = DD::NQ, NRED = DD::NRED;
+    const int pair = blockIdx.y;
+    const PairState st = a.state[pair];
+    if (!a.ignore_status && st.status != PAIR_ACTIVE) return;
+
+    double R[D][D], t[D];
+    if (a.T_override) {
+        const double* T = a.T_override + (size_t)pair * (D + 1) * (D + 1);
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) R[i][j] = T[i * (D + 1) + j];
+            t[i] = T[i * (D + 1) + D];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) R[i][j] = st.R[i * 3 + j];
+            t[i] = st.t[i];
+        }
+    }
+    const CloudMeta ms = a.src_meta[pair];
+    const CloudMeta mt = a.tgt_meta[pair];
+    int begin = ms.pt_begin, end = ms.pt_end;
+    if (a.slice_begin >= 0) { begin = max(begin, a.slice_begin); end = min(end, a.slice_end); }
+    const int nx = mt.dims[0], ny = mt.dims[1], nz = mt.dims[2];
+    const double cover1 = mt.h * (1.0 - 1e-9);
+    const int rho_max = max(1, (int)ceil(a.d_max / cover1));
+    const double d2cap = a.d_max * a.d_max * (1.0 + 1e-9);
+
+    AccT acc[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) acc[i] = AccT(0);
+    double loss_acc = 0.0;
+    int cnt = 0;
+
+    for (int it = 0; it < a.ppt; ++it) {
+        const int s = begin + (blockIdx.x * a.ppt + it) * OBJ_THREADS + threadIdx.x;
+        if (s >= end) break;
+        const PRec<Real> p = a.src_spts[s];
+        double pp[3] = {0.0, 0.0, 0.0};  // p' = R p + t (gicp.py:119)
+        {
+            const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                double v = R[i][0] * px + R[i][1] * py + t[i];
+                if constexpr (D == 3) v += R[i][2] * pz;
+                pp[i] = v;
+            }
+        }
+        // ---- 1-NN in the target grid, bounded by d_max (exactly equivalent to the unbounded
+        //      query + gate of gicp.py:132-138, SURVEY appendix A rule 6) ----
+        const int cx = cell_coord(pp[0], mt.origin[0], mt.inv_h);
+        const int cy = cell_coord(pp[1], mt.origin[1], mt.inv_h);
+        const int cz = (D == 3) ? cell_coord(pp[2], mt.origin[2], mt.inv_h) : 0;
+        double bestd = d2cap;
+        int besti = INT_MAX, bestpos = -1;
+        const float fx = (float)pp[0], fy = (float)pp[1], fz = (float)pp[2];
+        const double P = fmax(fabs(pp[0]), fmax(fabs(pp[1]), fabs(pp[2])));
+        float thr32 = __double2float_ru(bestd * (1.0 + 1e-6) + 4e-7 * sqrt(bestd) * P + 1e-30);
+        for (int rho = 1; rho <= rho_max; ++rho) {
+            const int y0 = max(cy - rho, 0), y1 = min(cy + rho, ny - 1);
+            const int z0 = (D == 3) ? max(cz - rho, 0) : 0, z1 = (D == 3) ? min(cz + rho, nz - 1) : 0;
+            for (int z = z0; z <= z1; ++z) {
+                for (int y = y0; y <= y1; ++y) {
+                    const bool inner_row = (rho > 1) && (abs(y - cy) < rho) && (D == 2 || abs(z - cz) < rho);
+                    const int n_runs = inner_row ? 2 : 1;
+                    for (int run = 0; run < n_runs; ++run) {
+                        int xlo, xhi;
+                        if (!inner_row) { xlo = max(cx - rho, 0); xhi = min(cx + rho, nx - 1); }
+                        else if (run == 0) { xlo = xhi = cx - rho; if (xlo < 0 || xlo > nx - 1) continue; }
+                        else { xlo = xhi = cx + rho; if (xlo < 0 || xlo > nx - 1) continue; }
+                        if (xhi < xlo) continue;
+                        const int rowbase = mt.cell_base + (z * ny + y) * nx;
+                        const int j0 = __ldg(a.tgt_cell_start + rowbase + xlo);
+                        const int j1 = __ldg(a.tgt_cell_start + rowbase + xhi + 1);
+                        for (int j = j0; j < j1; ++j) {
+                            const PRec<Real> c = a.tgt_spts[j];
+                            bool pass = true;
+                            if (sizeof(Real) == 4) {
+                                const float dx = (float)c.x - fx, dy = (float)c.y - fy, dz = (float)c.z - fz;
+                                pass = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr32;
+                            }
+                            if (pass) {
+                                const double e2 = exact_d2((double)c.x - pp[0], (double)c.y - pp[1],
+                                                           (double)c.z - pp[2]);
+                                const int ci = (int)c.idx;
+                                if (e2 < bestd || (e2 == bestd && ci < besti)) {
+                                    bestd = e2; besti = ci; bestpos = j;
+                                    thr32 = __double2float_ru(bestd * (1.0 + 1e-6) + 4e-7 * sqrt(bestd) * P + 1e-30);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            const double cover = rho * cover1;
+            if ((besti != INT_MAX && bestd <= cover * cover) || cover >= a.d_max) break;
+        }
+        const double dist = (besti != INT_MAX) ? sqrt(bestd) : INFINITY;
+        const bool matched = (besti != INT_MAX) && !(dist > a.d_max);  // gicp.py:136 rejects d > d_max
+        const size_t out_row = (size_t)ms.pt_begin + (size_t)p.idx;
+        if (a.out_idx) a.out_idx[out_row] = matched ? besti : -1;
+        if (a.out_dist) a.out_dist[out_row] = dist;
+        if (!matched) {
+            if (a.out_W) {
+                for (int i = 0; i < D * D; ++i) a.out_W[out_row * D * D + i] = 0.0;
+            }
+            continue;
+        }
+        // ---- W = inv(C_tgt[j] + R C_src[i] R^T), e = q - p' ----
+        const PRec<Real> q = a.tgt_spts[bestpos];
+        double Cs[NS], M[NS], W[NS], e[D], v[D];
+        {
+            const Real* cs = a.src_cov + (size_t)s * NS;
+            const Real* ct = a.tgt_cov + (size_t)bestpos * NS;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) { Cs[i] = (double)cs[i]; M[i] = (double)ct[i]; }
+        }
+        if constexpr (D == 3) {
+            const double C[3][3] = {{Cs[0], Cs[1], Cs[2]}, {Cs[1], Cs[3], Cs[4]}, {Cs[2], Cs[4], Cs[5]}};
+            double A[3][3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) A[i][j] = R[i][0] * C[0][j] + R[i][1] * C[1][j] + R[i][2] * C[2][j];
+            int k = 0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = i; j < 3; ++j) M[k++] += A[i][0] * R[j][0] + A[i][1] * R[j][1] + A[i][2] * R[j][2];
+            sym_inv3(M, W);
+            e[0] = (double)q.x - pp[0]; e[1] = (double)q.y - pp[1]; e[2] = (double)q.z - pp[2];
+            v[0] = W[0] * e[0] + W[1] * e[1] + W[2] * e[2];
+            v[1] = W[1] * e[0] + W[3] * e[1] + W[4] * e[2];
+            v[2] = W[2] * e[0] + W[4] * e[1] + W[5] * e[2];
+        } else {
+            const double C[2][2] = {{Cs[0], Cs[1]}, {Cs[1], Cs[2]}};
+            double A[2][2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) A[i][j] = R[i][0] * C[0][j] + R[i][1] * C[1][j];
+            M[0] += A[0][0] * R[0][0] + A[0][1] * R[0][1];
+            M[1] += A[0][0] * R[1][0] + A[0][1] * R[1][1];
+            M[2] += A[1][0] * R[1][0] + A[1][1] * R[1][1];
+            sym_inv2(M, W);
+            e[0] = (double)q.x - pp[0]; e[1] = (double)q.y - pp[1];
+            v[0] = W[0] * e[0] + W[1] * e[1];
+            v[1] = W[1] * e[0] + W[2] * e[1];
+        }
+        double li = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) li += e[i] * v[i];
+        loss_acc += li;
+        ++cnt;
+        if (a.out_W) {
+            double* o = a.out_W + out_row * D * D;
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j < D; ++j) o[i * D + j] = W[symidx(D, i, j)];
+        }
+        // ---- accumulate the reduced form ----
+        AccT pt[NP], Wa[NS], va[D];
+        pt[0] = AccT(1);
+#pragma unroll
+        for (int i = 0; i < D; ++i) { pt[1 + i] = (AccT)(pp[i] - st.mu[i]); va[i] = (AccT)v[i]; }
+#pragma unroll
+        for (int i = 0; i < NS; ++i) Wa[i] = (AccT)W[i];
+        {
+            int ab = 0;
+#pragma unroll
+            for (int i = 0; i < NP; ++i)
+#pragma unroll
+                for (int j = i; j < NP; ++j) {
+                    const AccT sij = pt[i] * pt[j];
+#pragma unroll
+                    for (int cd = 0; cd < NS; ++cd) acc[ab * NS + cd] += sij * Wa[cd];
+                    ++ab;
+                }
+#pragma unroll
+            for (int c = 0; c < D; ++c)
+#pragma unroll
+                for (int i = 0; i < NP; ++i) acc[NH + c * NP + i] += va[c] * pt[i];
+        }
+    }
+
+    // ---- block reduction: warp shuffles, then the warps' sums in fixed order in fp64 ----
+    __shared__ double s_red[OBJ_THREADS / 32][NQ + 2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+        const AccT r = warp_sum(acc[i]);
+        if (lane == 0) s_red[warp][i] = (double)r;
+    }
+    {
+        const double l = warp_sum(loss_acc);
+        const int c = warp_sum(cnt);
+        if (lane == 0) { s_red[warp][NQ] = l; s_red[warp][NQ + 1] = (double)c; }
+    }
+    __syncthreads();
+    if (threadIdx.x < NRED) {
+        double r = 0.0;
+        if (threadIdx.x < NQ + 2) {
+#pragma unroll
+            for (int w = 0; w < OBJ_THREADS / 32; ++w) r += s_red[w][threadIdx.x];
+        }
+        a.partial[((size_t)pair * a.blocks_per_pair + blockIdx.x) * NRED + threadIdx.x] = r;
+    }
+}
+
+}  // namespace gicp

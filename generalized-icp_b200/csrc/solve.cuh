@@ -1,0 +1,349 @@
+// K4: per-pair tail of one outer iteration.  Replaces fmin_cg (gicp.py:152) and the
+// convergence / bookkeeping block gicp.py:153-167.
+//   1. sums the blocks' partial reductions of K3 in a fixed order (deterministic),
+//   2. minimises the frozen inner objective  f(Z) = c - 2<G,Z> + <Z, H Z>,  Z = [dt | dR - I],
+//      over (dt, dR in SO(D)) by Levenberg-Marquardt on the (D + D(D-1)/2)-parameter normal
+//      equations  2 J^T H J  (3x3 in 2-D, 6x6 in 3-D), to convergence - the well-defined target
+//      of the reference's "minimise loss with W fixed",
+//   3. applies the stop rule |last - min_loss| < tolerance BEFORE updating T (gicp.py:160-167),
+//      records the history and updates the pair's transform.
+#pragma once
+#include "common.cuh"
+
+namespace gicp {
+
+template <int D> struct Reduced {
+    using DD = Dim<D>;
+    const double* Hq;  // [NAB][NS]
+    const double* G;   // [D][NP]
+    double c;
+    __device__ double H(int a, int b, int c_, int d) const {
+        return Hq[symidx(DD::NP, a, b) * DD::NS + symidx(D, c_, d)];
+    }
+    // out[c][a] = sum_{d,b} H(a,b,c,d) Z[d][b]
+    __device__ void apply(const double Z[D][D + 1], double out[D][D + 1]) const {
+        for (int c_ = 0; c_ < D; ++c_)
+            for (int a = 0; a < DD::NP; ++a) {
+                double s = 0.0;
+                for (int d = 0; d < D; ++d)
+                    for (int b = 0; b < DD::NP; ++b) s += H(a, b, c_, d) * Z[d][b];
+                out[c_][a] = s;
+            }
+    }
+    __device__ double eval(const double Z[D][D + 1]) const {
+        double HZ[D][D + 1];
+        apply(Z, HZ);
+        double lin = 0.0, quad = 0.0;
+        for (int c_ = 0; c_ < D; ++c_)
+            for (int a = 0; a < DD::NP; ++a) {
+                lin += G[c_ * DD::NP + a] * Z[c_][a];
+                quad += Z[c_][a] * HZ[c_][a];
+            }
+        return c - 2.0 * lin + quad;
+    }
+};
+
+template <int N> __device__ inline bool cholesky_solve(double A[N][N], double b[N]) {
+    // in-place LL^T; returns false when A is not positive definite
+    for (int j = 0; j < N; ++j) {
+        double d = A[j][j];
+        for (int k = 0; k < j; ++k) d -= A[j][k] * A[j][k];
+        if (!(d > 0.0) || !isfinite(d)) return false;
+        d = sqrt(d);
+        A[j][j] = d;
+        for (int i = j + 1; i < N; ++i) {
+            double s = A[i][j];
+            for (int k = 0; k < j; ++k) s -= A[i][k] * A[j][k];
+            A[i][j] = s / d;
+        }
+    }
+    for (int i = 0; i < N; ++i) {
+        double s = b[i];
+        for (int k = 0; k < i; ++k) s -= A[i][k] * b[k];
+        b[i] = s / A[i][i];
+    }
+    for (int i = N - 1; i >= 0; --i) {
+        double s = b[i];
+        for (int k = i + 1; k < N; ++k) s -= A[k][i] * b[k];
+        b[i] = s / A[i][i];
+    }
+    return true;
+}
+
+__device__ inline void rodrigues(const double w[3], double R[3][3]) {
+    const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+    double A, B;  // R = I + A K + B K^2
+    if (th2 < 1e-16) { A = 1.0 - th2 / 6.0; B = 0.5 - th2 / 24.0; }
+    else { const double th = sqrt(th2); A = sin(th) / th; B = (1.0 - cos(th)) / th2; }
+    const double K[3][3] = {{0, -w[2], w[1]}, {w[2], 0, -w[0]}, {-w[1], w[0], 0}};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double k2 = 0.0;
+            for (int k = 0; k < 3; ++k) k2 += K[i][k] * K[k][j];
+            R[i][j] = (i == j ? 1.0 : 0.0) + A * K[i][j] + B * k2;
+        }
+}
+
+// dR for the candidate step; dim 2 keeps the accumulated angle so dR is always an exact rot(dtheta)
+template <int D>
+__device__ inline void compose_rotation(const double* step_rot, const double dR[D][D], double dtheta,
+                                        double dRn[D][D], double* dtheta_n) {
+    if constexpr (D == 2) {
+        const double th = dtheta + step_rot[0];
+        double s, c;
+        sincos(th, &s, &c);
+        dRn[0][0] = c; dRn[0][1] = -s; dRn[1][0] = s; dRn[1][1] = c;
+        *dtheta_n = th;
+    } else {
+        double E[3][3];
+        rodrigues(step_rot, E);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) dRn[i][j] = E[i][0] * dR[0][j] + E[i][1] * dR[1][j] + E[i][2] * dR[2][j];
+        *dtheta_n = 0.0;
+    }
+}
+
+// Minimise the reduced form.  On return dR, dt (centred frame) and the minimum value.
+template <int D>
+__device__ void inner_solve(const Reduced<D>& red, int max_it, double dR[D][D], double dt[D], double* dtheta,
+                            double* fmin) {
+    using DD = Dim<D>;
+    constexpr int NP = DD::NP, NPAR = DD::NPAR, NROT = NPAR - D;
+    for (int i = 0; i < D; ++i) {
+        dt[i] = 0.0;
+        for (int j = 0; j < D; ++j) dR[i][j] = (i == j) ? 1.0 : 0.0;
+    }
+    *dtheta = 0.0;
+    double Z[D][D + 1];
+    for (int i = 0; i < D; ++i)
+        for (int a = 0; a < NP; ++a) Z[i][a] = 0.0;
+    double f = red.c;
+    double lam = 1e-9;
+    for (int it = 0; it < max_it; ++it) {
+        // gradient wrt Z
+        double Gam[D][D + 1];
+        red.apply(Z, Gam);
+        for (int c = 0; c < D; ++c)
+            for (int a = 0; a < NP; ++a) Gam[c][a] = 2.0 * (Gam[c][a] - red.G[c * NP + a]);
+        // tangent directions dZ_x: translations, then rotations [0 | E_k dR]
+        double dZ[NPAR][D][D + 1];
+        for (int x = 0; x < NPAR; ++x)
+            for (int c = 0; c < D; ++c)
+                for (int a = 0; a < NP; ++a) dZ[x][c][a] = 0.0;
+        for (int c = 0; c < D; ++c) dZ[c][c][0] = 1.0;
+        if constexpr (D == 2) {
+            // E = [[0,-1],[1,0]]
+            for (int j = 0; j < 2; ++j) { dZ[2][0][1 + j] = -dR[1][j]; dZ[2][1][1 + j] = dR[0][j]; }
+        } else {
+            for (int k = 0; k < 3; ++k) {
+                const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;  // (E_k M)[k1] = -M[k2], (E_k M)[k2] = M[k1]
+                for (int j = 0; j < 3; ++j) { dZ[3 + k][k1][1 + j] = -dR[k2][j]; dZ[3 + k][k2][1 + j] = dR[k1][j]; }
+            }
+        }
+        double g[NPAR], A[NPAR][NPAR], HdZ[NPAR][D][D + 1];
+        for (int x = 0; x < NPAR; ++x) {
+            red.apply(dZ[x], HdZ[x]);
+            double s = 0.0;
+            for (int c = 0; c < D; ++c)
+                for (int a = 0; a < NP; ++a) s += Gam[c][a] * dZ[x][c][a];
+            g[x] = s;
+        }
+        double gmax = 0.0;
+        for (int x = 0; x < NPAR; ++x) {
+            gmax = fmax(gmax, fabs(g[x]));
+            for (int y = 0; y <= x; ++y) {
+                double s = 0.0;
+                for (int c = 0; c < D; ++c)
+                    for (int a = 0; a < NP; ++a) s += dZ[x][c][a] * HdZ[y][c][a];
+                A[x][y] = A[y][x] = 2.0 * s;
+            }
+        }
+        if (!(gmax > 1e-11 * fmax(1.0, fabs(f)))) break;
+        bool accepted = false;
+        double stepmax = 0.0;
+        for (int tries = 0; tries < 40; ++tries) {
+            double L[NPAR][NPAR], step[NPAR];
+            for (int x = 0; x < NPAR; ++x) {
+                for (int y = 0; y < NPAR; ++y) L[x][y] = A[x][y];
+                L[x][x] += lam * A[x][x];
+                step[x] = -g[x];
+            }
+            if (!cholesky_solve<NPAR>(L, step)) { lam = fmax(lam * 10.0, 1e-6); continue; }
+            double dRn[D][D], dtn[D], thn, Zn[D][D + 1];
+            compose_rotation<D>(step + D, dR, *dtheta, dRn, &thn);
+            for (int c = 0; c < D; ++c) {
+                dtn[c] = dt[c] + step[c];
+                Zn[c][0] = dtn[c];
+                for (int j = 0; j < D; ++j) Zn[c][1 + j] = dRn[c][j] - (c == j ? 1.0 : 0.0);
+            }
+            const double fn = red.eval(Zn);
+            double pred = 0.0;
+            for (int x = 0; x < NPAR; ++x) pred -= g[x] * step[x];
+            if (fn <= f || pred <= 1e-11 * fabs(f)) {
+                for (int c = 0; c < D; ++c) {
+                    dt[c] = dtn[c];
+                    for (int j = 0; j < D; ++j) dR[c][j] = dRn[c][j];
+                    for (int a = 0; a < NP; ++a) Z[c][a] = Zn[c][a];
+                }
+                *dtheta = thn;
+                f = fn;
+                lam = fmax(lam * 0.1, 1e-12);
+                accepted = true;
+                for (int x = 0; x < NPAR; ++x) stepmax = fmax(stepmax, fabs(step[x]));
+                break;
+            }
+            lam = fmax(lam * 10.0, 1e-9);
+        }
+        (void)NROT;
+        if (!accepted || stepmax < 1e-14) break;
+    }
+    *fmin = f;
+}
+
+struct SolveArgs {
+    const double* partial;  // [n_pairs][blocks_per_pair][NRED]
+    int blocks_per_pair;
+    int n_pairs;
+    double* sum_out;        // if set: write the summed rows [n_pairs][NRED] (+mu) and return
+    PairState* state;
+    int max_iterations;
+    int inner_max_iterations;
+    double tolerance;
+    double* d_T;            // [n_pairs][(D+1)^2]
+    int* d_n_outer;
+    int* d_converged;
+    double* d_loss_hist;    // optional [n_pairs][max_iterations]
+    double* d_T_hist;       // optional [n_pairs][max_iterations+1][(D+1)^2]
+    int* d_inliers;         // optional [n_pairs][max_iterations]
+    int* n_active;
+};
+
+template <int D> __device__ inline void write_T(double* out, const PairState& st) {
+    for (int i = 0; i < D; ++i) {
+        for (int j = 0; j < D; ++j) out[i * (D + 1) + j] = st.R[i * 3 + j];
+        out[i * (D + 1) + D] = st.t[i];
+    }
+    for (int j = 0; j < D; ++j) out[D * (D + 1) + j] = 0.0;
+    out[D * (D + 1) + D] = 1.0;
+}
+
+constexpr int SOLVE_WARPS = 4;
+
+template <int D>
+__global__ void __launch_bounds__(SOLVE_WARPS * 32) solve_kernel(const SolveArgs a) {
+    using DD = Dim<D>;
+    constexpr int NRED = DD::NRED, NQ = DD::NQ, NP = DD::NP;
+    __shared__ double s_red[SOLVE_WARPS][NRED];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = blockIdx.x * SOLVE_WARPS + warp;
+    if (pair >= a.n_pairs) return;
+    PairState st = a.state[pair];
+    if (!a.sum_out && st.status != PAIR_ACTIVE) return;
+    for (int j = lane; j < NRED; j += 32) {
+        double s = 0.0;
+        const double* p = a.partial + (size_t)pair * a.blocks_per_pair * NRED + j;
+        for (int b = 0; b < a.blocks_per_pair; ++b) s += p[(size_t)b * NRED];
+        s_red[warp][j] = s;
+    }
+    __syncwarp();
+    if (a.sum_out) {
+        for (int j = lane; j < NRED; j += 32) {
+            double v = s_red[warp][j];
+            if (j >= NQ + 2 && j < NQ + 2 + D) v = st.mu[j - NQ - 2];
+            a.sum_out[(size_t)pair * NRED + j] = v;
+        }
+        return;
+    }
+    if (lane != 0) return;
+    Reduced<D> red;
+    red.Hq = s_red[warp];
+    red.G = s_red[warp] + DD::NH;
+    red.c = s_red[warp][NQ];
+    const int inliers = (int)(s_red[warp][NQ + 1] + 0.5);
+    double dR[D][D], dtc[D], dtheta, fmin;
+    inner_solve<D>(red, a.inner_max_iterations, dR, dtc, &dtheta, &fmin);
+
+    const int it = st.iter;
+    const double delta = fabs(st.last_loss - fmin);  // gicp.py:155
+    if (a.d_loss_hist) a.d_loss_hist[(size_t)pair * a.max_iterations + it] = fmin;
+    if (a.d_inliers) a.d_inliers[(size_t)pair * a.max_iterations + it] = inliers;
+    a.d_n_outer[pair] = it + 1;
+    if (delta < a.tolerance) {  // gicp.py:160-162: stop WITHOUT applying this iteration's offset
+        st.status = PAIR_CONVERGED;
+        st.converged_at = it;
+    } else {
+        st.last_loss = fmin;
+        // un-centre:  r = q - dR p' - dt,  dt = dt_c - (dR - I) mu
+        double dt[D];
+        for (int i = 0; i < D; ++i) {
+            double s = dtc[i];
+            for (int j = 0; j < D; ++j) s -= (dR[i][j] - (i == j ? 1.0 : 0.0)) * st.mu[j];
+            dt[i] = s;
+        }
+        // T_{k+1} = [dR R_k | dR t_k + dt]
+        double Rn[D][D], tn[D];
+        for (int i = 0; i < D; ++i) {
+            double s = dt[i];
+            for (int j = 0; j < D; ++j) s += dR[i][j] * st.t[j];
+            tn[i] = s;
+        }
+        if constexpr (D == 2) {
+            st.theta += dtheta;  // the reference rebuilds T from (tx, ty, theta), gicp.py:166
+            double s, c;
+            sincos(st.theta, &s, &c);
+            Rn[0][0] = c; Rn[0][1] = -s; Rn[1][0] = s; Rn[1][1] = c;
+        } else {
+            for (int i = 0; i < D; ++i)
+                for (int j = 0; j < D; ++j) {
+                    double s = 0.0;
+                    for (int k = 0; k < D; ++k) s += dR[i][k] * st.R[k * 3 + j];
+                    Rn[i][j] = s;
+                }
+        }
+        for (int i = 0; i < D; ++i) {
+            for (int j = 0; j < D; ++j) st.R[i * 3 + j] = Rn[i][j];
+            st.t[i] = tn[i];
+        }
+        st.iter = it + 1;
+        if (a.d_T_hist) write_T<D>(a.d_T_hist + ((size_t)pair * (a.max_iterations + 1) + it + 1) * (D + 1) * (D + 1), st);
+        if (st.iter >= a.max_iterations) st.status = PAIR_MAXITER;
+    }
+    write_T<D>(a.d_T + (size_t)pair * (D + 1) * (D + 1), st);
+    a.d_converged[pair] = st.converged_at;
+    a.state[pair] = st;
+    if (st.status != PAIR_ACTIVE) atomicSub(a.n_active, 1);
+    (void)NP;
+}
+
+// initialise the per-pair state (gicp.py:107-110): T = T0 or identity, last_loss = inf
+template <int D>
+__global__ void init_state_kernel(PairState* state, const double* T0, const double* tgt_bbox, int n_pairs,
+                                  double* d_T, double* d_T_hist, int max_iterations, int* d_n_outer,
+                                  int* d_converged) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= n_pairs) return;
+    PairState st;
+    for (int i = 0; i < 9; ++i) st.R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    for (int i = 0; i < 3; ++i) { st.t[i] = 0.0; st.mu[i] = 0.5 * (tgt_bbox[pair * 6 + i] + tgt_bbox[pair * 6 + 3 + i]); }
+    st.theta = 0.0;
+    if (T0) {
+        const double* T = T0 + (size_t)pair * (D + 1) * (D + 1);
+        for (int i = 0; i < D; ++i) {
+            for (int j = 0; j < D; ++j) st.R[i * 3 + j] = T[i * (D + 1) + j];
+            st.t[i] = T[i * (D + 1) + D];
+        }
+        if (D == 2) st.theta = atan2(st.R[3], st.R[0]);
+    }
+    st.last_loss = INFINITY;
+    st.iter = 0;
+    st.status = PAIR_ACTIVE;
+    st.converged_at = -1;
+    st.pad = 0;
+    state[pair] = st;
+    if (d_T) write_T<D>(d_T + (size_t)pair * (D + 1) * (D + 1), st);
+    if (d_T_hist) write_T<D>(d_T_hist + (size_t)pair * (max_iterations + 1) * (D + 1) * (D + 1), st);
+    if (d_n_outer) d_n_outer[pair] = 0;
+    if (d_converged) d_converged[pair] = -1;
+}
+
+}  // namespace gicp

@@ -1,0 +1,216 @@
+"""Host side of the engine: a thin object over the C ABI (include/gicp_b200.h).
+
+PyTorch is used for device memory and streams only; every computation happens
+in libgicp_b200.so.  Method names mirror the stages of the reference's
+``gicp()`` (python-implementation/gicp.py:78-174)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GicpParams  # noqa: F401
+
+SOURCE, TARGET = 0, 1
+_STORAGE = {"f32": (0, torch.float32), "f64": (1, torch.float64)}
+
+
+@dataclass
+class RegistrationResult:
+    """Device-resident outputs of :meth:`GicpEngine.register` (one row per pair)."""
+    T: torch.Tensor            # (P, d+1, d+1) f64   final transform (gicp.py:174 [0])
+    n_outer: torch.Tensor      # (P,) i32            outer iterations executed
+    converged_at: torch.Tensor  # (P,) i32           "Converged at iteration k" (gicp.py:161) or -1
+    loss_hist: torch.Tensor | None   # (P, max_it) f64 min_loss per iteration (gicp.py:154)
+    T_hist: torch.Tensor | None      # (P, max_it+1, d+1, d+1) all_transformations (gicp.py:108,167)
+    inliers: torch.Tensor | None     # (P, max_it) i32
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class GicpEngine:
+    """One engine = one C handle, bound to one device, one dimension and one storage type."""
+
+    def __init__(self, dim: int, storage: str = "f32", device: int | None = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("GicpEngine needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.dim = int(dim)
+        self.storage = storage
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self._storage_code, self.dtype = _STORAGE[storage]
+        self._h = C.c_void_p()
+        _lib.check(self.lib.gicpCreate(C.byref(self._h), self.device_index, self.dim, self._storage_code))
+        self.params = GicpParams()
+        _lib.check(self.lib.gicpDefaultParams(C.byref(self.params)))
+        self._keep = {}
+        self._n = {SOURCE: (0, 0), TARGET: (0, 0)}
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.gicpDestroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- parameters (names of gicp.py:78 plus the engine's own) ----
+    def set_params(self, **kw):
+        for k, v in kw.items():
+            if not hasattr(self.params, k):
+                raise TypeError(f"unknown parameter {k!r}")
+            setattr(self.params, k, v)
+        _lib.check(self.lib.gicpSetParams(self._h, C.byref(self.params)))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _prep(self, points, offsets):
+        if not isinstance(points, torch.Tensor):
+            points = torch.as_tensor(np.ascontiguousarray(np.asarray(points)), device=self.device)
+        points = points.to(device=self.device, dtype=self.dtype).contiguous()
+        if points.ndim != 2 or points.shape[1] != self.dim:
+            raise ValueError(f"expected (N, {self.dim}) points, got {tuple(points.shape)}")
+        if offsets is None:
+            offsets = [0, points.shape[0]]
+        off = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64))
+        if off[-1] != points.shape[0]:
+            raise ValueError("offsets[-1] must equal the number of points")
+        return points, off
+
+    def _set(self, which, points, offsets):
+        points, off = self._prep(points, offsets)
+        self._keep[which] = points  # the library reads the caller's array later (covariance stage)
+        self._n[which] = (points.shape[0], len(off) - 1)
+        fn = self.lib.gicpSetTarget if which == TARGET else self.lib.gicpSetSource
+        _lib.check(fn(self._h, _ptr(points), off.ctypes.data_as(C.POINTER(C.c_int64)), len(off) - 1, self._stream()))
+
+    def set_target(self, points, offsets=None):
+        """Grid build + covariances of the target(s): KDTree + compute_covariance_matrix, gicp.py:104."""
+        self._set(TARGET, points, offsets)
+
+    def set_source(self, points, offsets=None):
+        """Grid build + covariances of the source(s): gicp.py:111."""
+        self._set(SOURCE, points, offsets)
+
+    # ---- the loop ----
+    def register(self, T0=None, history=True) -> RegistrationResult:
+        n_pairs = self._n[SOURCE][1]
+        d1 = self.dim + 1
+        mi = int(self.params.max_iterations)
+        dev = self.device
+        T = torch.empty((n_pairs, d1, d1), dtype=torch.float64, device=dev)
+        n_outer = torch.empty((n_pairs,), dtype=torch.int32, device=dev)
+        conv = torch.empty((n_pairs,), dtype=torch.int32, device=dev)
+        loss = torch.full((n_pairs, mi), float("nan"), dtype=torch.float64, device=dev) if history else None
+        T_hist = torch.full((n_pairs, mi + 1, d1, d1), float("nan"), dtype=torch.float64, device=dev) if history else None
+        inl = torch.zeros((n_pairs, mi), dtype=torch.int32, device=dev) if history else None
+        t0p = None
+        if T0 is not None:
+            T0 = np.ascontiguousarray(np.asarray(T0, dtype=np.float64).reshape(n_pairs, d1, d1))
+            t0p = T0.ctypes.data_as(C.POINTER(C.c_double))
+        _lib.check(self.lib.gicpRegister(self._h, t0p, _ptr(T), _ptr(n_outer), _ptr(conv), _ptr(loss), _ptr(T_hist),
+                                         _ptr(inl), self._stream()))
+        return RegistrationResult(T, n_outer, conv, loss, T_hist, inl)
+
+    # ---- stage entry points ----
+    def knn(self, which, with_dist=True):
+        n = self._n[which][0]
+        k = int(self.params.k)
+        idx = torch.empty((n, k), dtype=torch.int32, device=self.device)
+        dist = torch.empty((n, k), dtype=torch.float64, device=self.device) if with_dist else None
+        _lib.check(self.lib.gicpKnn(self._h, which, _ptr(idx), _ptr(dist), self._stream()))
+        return idx, dist
+
+    def covariances(self, which):
+        n = self._n[which][0]
+        out = torch.empty((n, self.dim, self.dim), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.gicpCovariances(self._h, which, _ptr(out), self._stream()))
+        return out
+
+    def _T_arg(self, T, lead=()):
+        n_pairs = self._n[SOURCE][1]
+        d1 = self.dim + 1
+        T = np.ascontiguousarray(np.asarray(T, dtype=np.float64).reshape(*lead, n_pairs, d1, d1))
+        return T, T.ctypes.data_as(C.POINTER(C.c_double))
+
+    def correspond(self, T, with_W=True):
+        n = self._n[SOURCE][0]
+        T, tp = self._T_arg(T)
+        idx = torch.empty((n,), dtype=torch.int32, device=self.device)
+        dist = torch.empty((n,), dtype=torch.float64, device=self.device)
+        W = torch.empty((n, self.dim, self.dim), dtype=torch.float64, device=self.device) if with_W else None
+        _lib.check(self.lib.gicpCorrespond(self._h, tp, _ptr(idx), _ptr(dist), _ptr(W), self._stream()))
+        return idx, dist, W
+
+    def normal_equations(self, T):
+        n_pairs = self._n[SOURCE][1]
+        T, tp = self._T_arg(T)
+        nred = 80 if self.dim == 3 else 32
+        out = np.zeros((n_pairs, nred), dtype=np.float64)
+        _lib.check(self.lib.gicpNormalEquations(self._h, tp, out.ctypes.data_as(C.POINTER(C.c_double)), self._stream()))
+        return out
+
+    def source_covariances_at(self, Ts):
+        Ts = np.asarray(Ts, dtype=np.float64)
+        n_T = Ts.shape[0]
+        T, tp = self._T_arg(Ts, lead=(n_T,))
+        n = self._n[SOURCE][0]
+        out = torch.empty((n_T, n, self.dim, self.dim), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.gicpSourceCovariancesAt(self._h, tp, n_T, _ptr(out), self._stream()))
+        return out
+
+    # ---- multi-GPU (sharded source, config 5) ----
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _lib.check(_lib.load().gicpCommGetUniqueId(buf))
+        return buf.raw
+
+    def comm_init(self, n_ranks, rank, unique_id: bytes):
+        _lib.check(self.lib.gicpCommInit(self._h, n_ranks, rank, C.create_string_buffer(unique_id, 128)))
+
+    def comm_destroy(self):
+        _lib.check(self.lib.gicpCommDestroy(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.gicpLaunchCount(self._h))
+
+
+def reduced_form_loss(red, dim, T_lin, T_eval):
+    """f(Z) = c - 2<G,Z> + <Z,HZ> with Z = [dt | dR - I] for the transform T_eval expressed
+    relative to the linearisation transform T_lin (layout: include/gicp_b200.h)."""
+    d = dim
+    NP, NS = d + 1, d * (d + 1) // 2
+    NAB = NP * (NP + 1) // 2
+    NH = NAB * NS
+    Hq = red[:NH].reshape(NAB, NS)
+    G = red[NH:NH + d * NP].reshape(d, NP)
+    c = red[NH + d * NP]
+    mu = red[NH + d * NP + 2:NH + d * NP + 2 + d]
+    dR = T_eval[:d, :d] @ np.linalg.inv(T_lin[:d, :d])
+    dt = T_eval[:d, d] - dR @ T_lin[:d, d]
+    dtc = dt + (dR - np.eye(d)) @ mu
+    Z = np.concatenate([dtc[:, None], dR - np.eye(d)], axis=1)          # (d, NP)
+
+    def sym(n, a, b):
+        a, b = min(a, b), max(a, b)
+        return a * n - a * (a - 1) // 2 + (b - a)
+
+    quad = 0.0
+    for a in range(NP):
+        for b in range(NP):
+            for cc in range(d):
+                for dd in range(d):
+                    quad += Z[cc, a] * Z[dd, b] * Hq[sym(NP, a, b), sym(d, cc, dd)]
+    return float(c - 2.0 * np.sum(G * Z) + quad)
