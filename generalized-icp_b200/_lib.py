@@ -11,7 +11,7 @@ SYMBOLS = [
     "gicpCreate", "gicpDestroy", "gicpGetLastError", "gicpVersion", "gicpDefaultParams", "gicpSetParams",
     "gicpSetTarget", "gicpSetSource", "gicpRegister", "gicpKnn", "gicpCovariances", "gicpCorrespond",
     "gicpNormalEquations", "gicpSourceCovariancesAt", "gicpCommGetUniqueId", "gicpCommInit", "gicpCommDestroy",
-    "gicpLaunchCount",
+    "gicpLaunchCount", "gicpProfile", "gicpProfileRead",
 ]
 
 
@@ -64,6 +64,8 @@ def load():
     lib.gicpCommDestroy.argtypes = [vp]
     lib.gicpLaunchCount.argtypes = [vp]
     lib.gicpLaunchCount.restype = i64
+    lib.gicpProfile.argtypes = [vp, C.c_int]
+    lib.gicpProfileRead.argtypes = [vp, dp, C.POINTER(i64)]
     _lib = lib
     return lib
 

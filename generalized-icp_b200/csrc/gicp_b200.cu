@@ -117,7 +117,7 @@ int load_nccl() {
         return fail("libnccl is missing a required symbol");
     return 0;
 }
-constexpr int NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_INT8 = 0;
+constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_INT8 = 0;
 
 }  // namespace
 
@@ -130,6 +130,20 @@ struct gicpContext {
     int* h_poll = nullptr;  // pinned
     cudaEvent_t poll_event = nullptr;
     int64_t launches = 0;
+    // per-stage CUDA-event timing (off by default): stage ids in include/gicp_b200.h
+    bool prof_on = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct ProfRec { int stage; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    cudaEvent_t prof_event() {
+        if (ev_used == ev_pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ev_pool.push_back(e);
+        }
+        return ev_pool[ev_used++];
+    }
     // sharded-source mode
     void* comm = nullptr;
     int n_ranks = 1, rank = 0;
@@ -137,10 +151,23 @@ struct gicpContext {
 
 namespace {
 
-size_t real_size(const gicpContext* h) { return h->storage == GICP_STORAGE_F32 ? 4 : 8; }
-size_t prec_size(const gicpContext* h) { return h->storage == GICP_STORAGE_F32 ? 16 : 32; }
 int ns_of(int dim) { return dim * (dim + 1) / 2; }
-int nred_of(int dim) { return dim == 3 ? GICP_NRED_3D : GICP_NRED_2D; }
+
+struct ProfScope {
+    gicpContext* h;
+    cudaStream_t st;
+    cudaEvent_t b = nullptr;
+    ProfScope(gicpContext* h_, int stage, cudaStream_t st_) : h(h_), st(st_) {
+        if (!h->prof_on) return;
+        cudaEvent_t a = h->prof_event();
+        b = h->prof_event();
+        cudaEventRecord(a, st);
+        h->prof_recs.push_back({stage, a, b});
+    }
+    ~ProfScope() {
+        if (b) cudaEventRecord(b, st);
+    }
+};
 
 template <int D, typename Real>
 int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, bool want_inv_perm, cudaStream_t st) {
@@ -148,7 +175,7 @@ int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, bool want
     const int64_t n = cs.n_total;
     long long budget = h->prm.max_cells_per_cloud;
     if (budget <= 0) {
-        budget = 4LL * cs.max_n;
+        budget = cs.max_n;
         if (budget < 4096) budget = 4096;
     }
     if (budget * (long long)nc > (1LL << 30)) {
@@ -172,6 +199,7 @@ int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, bool want
     CU(h->vals_alt.ensure((size_t)std::max<int64_t>(n, 1) * 4));
     const Real* pts = static_cast<const Real*>(cs.raw);
     const int* offs = cs.d_offsets.as<int>();
+    ProfScope prof(h, GICP_STAGE_GRID, st);
 
     bbox_partial_kernel<D, Real><<<dim3(chunks, nc), BBOX_THREADS, 0, st>>>(pts, offs, h->bbox_part.as<double>(), chunks);
     grid_meta_kernel<D><<<(nc + 127) / 128, 128, 0, st>>>(h->bbox_part.as<double>(), chunks, offs, nc, h_target, budget,
@@ -292,6 +320,7 @@ int launch_knn(gicpContext* h, CloudSet& cs, int* d_idx, double* d_dist, cudaStr
     const int bx = (span + KNN_THREADS - 1) / KNN_THREADS;
     const size_t smem = 128 + (size_t)KNN_WARPS * KNN_STAGE_BYTES;
     dim3 grid(bx, cs.n_clouds);
+    ProfScope prof(h, GICP_STAGE_KNN_COV, st);
 #define KNN_LAUNCH(KC)                                                                                       \
     do {                                                                                                     \
         CU(cudaFuncSetAttribute(knn_cov_kernel<D, Real, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
@@ -479,7 +508,11 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
     *h->h_poll = np;
     const int poll_every = 2;
     for (int it = 0; it < h->prm.max_iterations; ++it) {
-        objective_kernel<D, Real><<<ogrid, OBJ_THREADS, 0, st>>>(oa);
+        {
+            ProfScope prof(h, GICP_STAGE_OBJECTIVE, st);
+            objective_kernel<D, Real><<<ogrid, OBJ_THREADS, 0, st>>>(oa);
+        }
+        ProfScope prof(h, GICP_STAGE_SOLVE, st);
         if (sharded) {
             SolveArgs s1 = sa;
             s1.sum_out = h->red.as<double>();
@@ -650,6 +683,7 @@ int gicpDestroy(gicpHandle h) {
                       &h->knn_idx_tmp, &h->state, &h->partial, &h->red, &h->T_dev, &h->n_active};
     for (DevBuf* b : bufs) b->release();
     if (h->h_poll) cudaFreeHost(h->h_poll);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
     return 0;
 }
@@ -751,5 +785,28 @@ int gicpCommDestroy(gicpHandle h) {
 }
 
 int64_t gicpLaunchCount(gicpHandle h) { return h ? h->launches : 0; }
+
+int gicpProfile(gicpHandle h, int enable) {
+    if (check(h)) return 1;
+    h->prof_on = enable != 0;
+    h->prof_recs.clear();
+    h->ev_used = 0;
+    return 0;
+}
+
+int gicpProfileRead(gicpHandle h, double ms_out[GICP_N_STAGES], int64_t count_out[GICP_N_STAGES]) {
+    if (check(h)) return 1;
+    CU(cudaDeviceSynchronize());
+    for (int i = 0; i < GICP_N_STAGES; ++i) { ms_out[i] = 0.0; count_out[i] = 0; }
+    for (auto& r : h->prof_recs) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, r.a, r.b));
+        ms_out[r.stage] += ms;
+        count_out[r.stage] += 1;
+    }
+    h->prof_recs.clear();
+    h->ev_used = 0;
+    return 0;
+}
 
 }  // extern "C"

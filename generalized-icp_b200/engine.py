@@ -182,6 +182,18 @@ class GicpEngine:
     def comm_destroy(self):
         _lib.check(self.lib.gicpCommDestroy(self._h))
 
+    STAGES = ("grid_build", "knn_cov", "objective", "solve")
+
+    def profile(self, enable=True):
+        _lib.check(self.lib.gicpProfile(self._h, int(bool(enable))))
+
+    def profile_read(self):
+        """{stage: (milliseconds, timed sections)} since the last read (device-synchronising)."""
+        ms = (C.c_double * 4)()
+        cnt = (C.c_int64 * 4)()
+        _lib.check(self.lib.gicpProfileRead(self._h, ms, cnt))
+        return {s: (float(ms[i]), int(cnt[i])) for i, s in enumerate(self.STAGES)}
+
     @property
     def launch_count(self):
         return int(self.lib.gicpLaunchCount(self._h))
