@@ -7,17 +7,35 @@
 
 namespace gicp {
 
-// One uniform grid per cloud.  Cells are numbered x-fastest so that the cells
-// (x0..x1, y, z) of one row are one contiguous run of the sorted point array.
+// One uniform grid per cloud.  Cells are numbered along a Morton (Z-order) curve whose bit
+// budget per axis follows the grid's extent (bits[a] = ceil(log2(dims[a]))), so that points that
+// are consecutive in the sorted array are spatially compact in all axes.  Each cell is one
+// contiguous run of the sorted point array (cell_start[code] .. cell_start[code + 1]).
 struct CloudMeta {
     double origin[3];
     double h;        // cell edge actually used (>= requested; enlarged to fit the cell budget)
     double inv_h;
     int dims[3];
+    int bits[3];     // Morton bits per axis
     int cell_base;   // first entry of this cloud in the shared cell_start table
     int pt_begin;    // row range of this cloud in the concatenated arrays
     int pt_end;
+    int lut_base;    // first entry of this cloud's per-axis Morton tables: lut[lut_base + axis * GICP_LUT_N + v]
 };
+constexpr int GICP_LUT_N = 1024;   // per axis (GICP_MAX_AXIS_BITS bits)
+
+// anisotropic Morton code: bit b of every axis that still has bits, x first
+__host__ __device__ __forceinline__ int morton_code(int x, int y, int z, int bx, int by, int bz) {
+    int code = 0, pos = 0;
+#pragma unroll
+    for (int b = 0; b < 10; ++b) {
+        if (b < bx) { code |= ((x >> b) & 1) << pos; ++pos; }
+        if (b < by) { code |= ((y >> b) & 1) << pos; ++pos; }
+        if (b < bz) { code |= ((z >> b) & 1) << pos; ++pos; }
+    }
+    return code;
+}
+constexpr int GICP_MAX_AXIS_BITS = 10;  // <= 1024 cells per axis
 
 // Sorted point record: coordinates + cloud-local index of the point in the
 // caller's array.  16 B (f32) / 32 B (f64): multiples of 16 B so that runs can be

@@ -61,12 +61,12 @@ struct DevBuf {
 };
 
 struct Grid {
-    DevBuf meta, cell_start, spts, inv_perm, bbox;
+    DevBuf meta, cell_start, spts, inv_perm, perm, bbox, lut;
     long long budget = 0;
     long long total_cells = 0;
     double h_target = 0;
     bool built = false;
-    void release() { meta.release(); cell_start.release(); spts.release(); inv_perm.release(); bbox.release(); }
+    void release() { meta.release(); cell_start.release(); spts.release(); inv_perm.release(); perm.release(); bbox.release(); lut.release(); }
 };
 
 struct CloudSet {
@@ -76,11 +76,11 @@ struct CloudSet {
     int64_t n_total = 0;
     int max_n = 0;
     DevBuf d_offsets;   // int32 [n_clouds+1]
-    Grid knn;           // grid used for the covariance neighbourhoods (and source ordering)
-    Grid nn;            // target only: grid of the correspondence search (may be unused -> knn)
-    bool nn_separate = false;
-    DevBuf cov_knn;     // covariances in knn-grid order
-    DevBuf cov_nn;      // covariances in nn-grid order (target, when nn_separate)
+    Grid knn;           // grid of the covariance neighbourhoods (cell ~ knn radius / 2)
+    Grid nn;            // grid of the correspondence search (cell ~ d_max / 2): the target is searched in it,
+                        // the source is only ORDERED by it (compact warps in K3)
+    DevBuf cov_knn;     // covariances in knn-grid order (written by K2)
+    DevBuf cov_nn;      // the same covariances in nn-grid order (read by K3)
     bool ready = false;
     void release() { d_offsets.release(); knn.release(); nn.release(); cov_knn.release(); cov_nn.release(); }
 };
@@ -126,7 +126,7 @@ struct gicpContext {
     gicpParams prm;
     CloudSet src, tgt;
     DevBuf keys, keys_alt, vals, vals_alt, cub_tmp, cell_count, bbox_part, knn_idx_tmp;
-    DevBuf state, partial, red, T_dev, n_active;
+    DevBuf state, partial, red, T_dev, n_active, prev_match;
     int* h_poll = nullptr;  // pinned
     cudaEvent_t poll_event = nullptr;
     int64_t launches = 0;
@@ -170,13 +170,14 @@ struct ProfScope {
 };
 
 template <int D, typename Real>
-int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, bool want_inv_perm, cudaStream_t st) {
+int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, bool want_inv_perm, bool idx_is_pos,
+               cudaStream_t st) {
     const int nc = cs.n_clouds;
     const int64_t n = cs.n_total;
     long long budget = h->prm.max_cells_per_cloud;
     if (budget <= 0) {
-        budget = cs.max_n;
-        if (budget < 4096) budget = 4096;
+        budget = 4096;  // Morton padding can cost up to 8x the occupied box
+        while (budget < 8LL * cs.max_n) budget <<= 1;
     }
     if (budget * (long long)nc > (1LL << 30)) {
         budget = (1LL << 30) / nc;
@@ -193,6 +194,7 @@ int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, bool want
     CU(h->cell_count.ensure((size_t)(g.total_cells + 1) * sizeof(int)));
     CU(g.spts.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(PRec<Real>)));
     if (want_inv_perm) CU(g.inv_perm.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(int)));
+    if (idx_is_pos) CU(g.perm.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(int)));
     CU(h->keys.ensure((size_t)std::max<int64_t>(n, 1) * 4));
     CU(h->keys_alt.ensure((size_t)std::max<int64_t>(n, 1) * 4));
     CU(h->vals.ensure((size_t)std::max<int64_t>(n, 1) * 4));
@@ -204,8 +206,10 @@ int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, bool want
     bbox_partial_kernel<D, Real><<<dim3(chunks, nc), BBOX_THREADS, 0, st>>>(pts, offs, h->bbox_part.as<double>(), chunks);
     grid_meta_kernel<D><<<(nc + 127) / 128, 128, 0, st>>>(h->bbox_part.as<double>(), chunks, offs, nc, h_target, budget,
                                                           g.meta.as<CloudMeta>(), g.bbox.as<double>());
+    CU(g.lut.ensure((size_t)nc * 3 * GICP_LUT_N * sizeof(int)));
+    morton_lut_kernel<<<dim3(3 * GICP_LUT_N / 256, nc), 256, 0, st>>>(g.meta.as<CloudMeta>(), g.lut.as<int>());
     CU(cudaMemsetAsync(h->cell_count.p, 0, (size_t)(g.total_cells + 1) * sizeof(int), st));
-    h->launches += 2;
+    h->launches += 3;
     if (n > 0) {
         const int bx = (cs.max_n + 255) / 256;
         cell_key_kernel<D, Real><<<dim3(bx, nc), 256, 0, st>>>(pts, g.meta.as<CloudMeta>(), h->keys.as<unsigned>(),
@@ -234,7 +238,8 @@ int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, bool want
         const int bx = (cs.max_n + 255) / 256;
         gather_sorted_kernel<D, Real><<<dim3(bx, nc), 256, 0, st>>>(pts, g.meta.as<CloudMeta>(), dv.Current(),
                                                                     g.spts.as<PRec<Real>>(),
-                                                                    want_inv_perm ? g.inv_perm.as<int>() : nullptr);
+                                                                    want_inv_perm ? g.inv_perm.as<int>() : nullptr,
+                                                                    idx_is_pos ? g.perm.as<int>() : nullptr);
         h->launches += 1;
     }
     CU(cudaGetLastError());
@@ -243,14 +248,14 @@ int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, bool want
 }
 
 template <int D, typename Real>
-__global__ void regather_cov_kernel(const CloudMeta* __restrict__ meta, const PRec<Real>* __restrict__ spts_dst,
+__global__ void regather_cov_kernel(const CloudMeta* __restrict__ meta, const int* __restrict__ perm_dst,
                                     const int* __restrict__ inv_perm_src, const Real* __restrict__ cov_src,
                                     Real* __restrict__ cov_dst) {
     constexpr int NS = Dim<D>::NS;
     const CloudMeta m = meta[blockIdx.y];
     const int s = m.pt_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= m.pt_end) return;
-    const int g = m.pt_begin + (int)spts_dst[s].idx;
+    const int g = m.pt_begin + perm_dst[s];
     const int ss = inv_perm_src[g];
 #pragma unroll
     for (int i = 0; i < NS; ++i) cov_dst[(size_t)s * NS + i] = cov_src[(size_t)ss * NS + i];
@@ -303,6 +308,7 @@ int launch_knn(gicpContext* h, CloudSet& cs, int* d_idx, double* d_dist, cudaStr
     KnnArgs<Real> a;
     a.meta = cs.knn.meta.as<CloudMeta>();
     a.cell_start = cs.knn.cell_start.as<int>();
+    a.lut = cs.knn.lut.as<int>();
     a.spts = cs.knn.spts.as<PRec<Real>>();
     a.raw = static_cast<const Real*>(cs.raw);
     a.cov_sorted = cs.cov_knn.as<Real>();
@@ -318,7 +324,7 @@ int launch_knn(gicpContext* h, CloudSet& cs, int* d_idx, double* d_dist, cudaStr
     const int span = (slice_b >= 0) ? (slice_e - slice_b) : cs.max_n;
     if (span <= 0) return 0;
     const int bx = (span + KNN_THREADS - 1) / KNN_THREADS;
-    const size_t smem = 128 + (size_t)KNN_WARPS * KNN_STAGE_BYTES;
+    const size_t smem = 128 + (size_t)KNN_WARPS * KNN_WARP_SMEM;
     dim3 grid(bx, cs.n_clouds);
     ProfScope prof(h, GICP_STAGE_KNN_COV, st);
 #define KNN_LAUNCH(KC)                                                                                       \
@@ -336,13 +342,18 @@ int launch_knn(gicpContext* h, CloudSet& cs, int* d_idx, double* d_dist, cudaStr
     return 0;
 }
 
+constexpr size_t OBJ_SMEM = 128 + (size_t)(OBJ_THREADS / 32) * OBJ_STAGE_BYTES;
+
+// cell edges; never smaller than (search radius)/8 so that a lane's ball spans <= 17 cells per axis
 double auto_knn_cell(const gicpContext* h) {
-    if (h->prm.knn_cell > 0) return h->prm.knn_cell;
-    return 0.5 * h->prm.max_distance_nearest_neighbors * (1.0 + 1e-6);
+    const double r = h->prm.max_distance_nearest_neighbors;
+    if (h->prm.knn_cell > 0) return std::max(h->prm.knn_cell, r / 8.0);
+    return 0.5 * r;
 }
 double auto_nn_cell(const gicpContext* h) {
-    if (h->prm.nn_cell > 0) return h->prm.nn_cell;
-    return 0.5 * h->prm.max_distance_correspondence * (1.0 + 1e-6);
+    const double r = h->prm.max_distance_correspondence;
+    if (h->prm.nn_cell > 0) return std::max(h->prm.nn_cell, r / 8.0);
+    return 0.5 * r;
 }
 
 template <int D, typename Real>
@@ -372,8 +383,7 @@ int set_cloud(gicpContext* h, int which, const void* d_points, const int64_t* h_
 
     const double h_knn = auto_knn_cell(h);
     const double h_nn = auto_nn_cell(h);
-    cs.nn_separate = (which == GICP_TARGET) && (fabs(h_nn - h_knn) > 0.2 * h_knn);
-    if (build_grid<D, Real>(h, cs, cs.knn, h_knn, cs.nn_separate, st)) return 1;
+    if (build_grid<D, Real>(h, cs, cs.knn, h_knn, true, false, st)) return 1;
     CU(cs.cov_knn.ensure((size_t)std::max<int64_t>(cs.n_total, 1) * ns_of(D) * sizeof(Real)));
 
     // covariances; in sharded mode the target slice is computed locally and all-gathered
@@ -398,14 +408,14 @@ int set_cloud(gicpContext* h, int which, const void* d_points, const int64_t* h_
         int rc = g_nccl.AllGather(basep + bytes * h->rank, basep, bytes, NCCL_INT8, h->comm, st);
         if (rc) return fail("ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
     }
-    if (cs.nn_separate) {
-        if (build_grid<D, Real>(h, cs, cs.nn, h_nn, false, st)) return 1;
+    {   // second ordering for the correspondence stage + the covariances carried over to it
+        if (build_grid<D, Real>(h, cs, cs.nn, h_nn, false, true, st)) return 1;
         CU(cs.cov_nn.ensure((size_t)std::max<int64_t>(cs.n_total, 1) * ns_of(D) * sizeof(Real)));
         if (cs.n_total > 0) {
             const int bx = (cs.max_n + 255) / 256;
             regather_cov_kernel<D, Real><<<dim3(bx, n_clouds), 256, 0, st>>>(
-                cs.nn.meta.as<CloudMeta>(), cs.nn.spts.as<PRec<Real>>(), cs.knn.inv_perm.as<int>(),
-                cs.cov_knn.as<Real>(), cs.cov_nn.as<Real>());
+                cs.nn.meta.as<CloudMeta>(), cs.nn.perm.as<int>(), cs.knn.inv_perm.as<int>(), cs.cov_knn.as<Real>(),
+                cs.cov_nn.as<Real>());
             h->launches += 1;
         }
     }
@@ -419,14 +429,17 @@ int objective_args(gicpContext* h, ObjArgs<Real>& a, int& blocks_per_pair, bool 
     CloudSet &S = h->src, &T = h->tgt;
     if (!S.ready || !T.ready) return fail("set source and target first");
     if (S.n_clouds != T.n_clouds) return fail("source has %d clouds, target %d", S.n_clouds, T.n_clouds);
-    const Grid& tg = T.nn_separate ? T.nn : T.knn;
-    a.src_meta = S.knn.meta.as<CloudMeta>();
-    a.src_spts = S.knn.spts.as<PRec<Real>>();
-    a.src_cov = S.cov_knn.as<Real>();
-    a.tgt_meta = tg.meta.as<CloudMeta>();
-    a.tgt_cell_start = tg.cell_start.as<int>();
-    a.tgt_spts = tg.spts.as<PRec<Real>>();
-    a.tgt_cov = T.nn_separate ? T.cov_nn.as<Real>() : T.cov_knn.as<Real>();
+    a.src_meta = S.nn.meta.as<CloudMeta>();
+    a.src_spts = S.nn.spts.as<PRec<Real>>();
+    a.src_cov = S.cov_nn.as<Real>();
+    a.src_perm = S.nn.perm.as<int>();
+    a.tgt_meta = T.nn.meta.as<CloudMeta>();
+    a.tgt_cell_start = T.nn.cell_start.as<int>();
+    a.tgt_lut = T.nn.lut.as<int>();
+    a.tgt_spts = T.nn.spts.as<PRec<Real>>();
+    a.tgt_cov = T.cov_nn.as<Real>();
+    a.tgt_perm = T.nn.perm.as<int>();
+    a.prev_match = nullptr;
     CU(h->state.ensure((size_t)S.n_clouds * sizeof(PairState)));
     a.state = h->state.as<PairState>();
     a.T_override = nullptr;
@@ -486,6 +499,10 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
     if (ensure_state<D, Real>(h, h_T0, d_T, d_T_hist, d_n_outer, d_converged, st)) return 1;
     CU(cudaMemcpyAsync(h->n_active.p, &np, sizeof(int), cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));
+    // last iteration's match per source point (bounds the next search); -1 = none yet
+    CU(h->prev_match.ensure((size_t)std::max<int64_t>(h->src.n_total, 1) * sizeof(int)));
+    CU(cudaMemsetAsync(h->prev_match.p, 0xFF, (size_t)std::max<int64_t>(h->src.n_total, 1) * sizeof(int), st));
+    oa.prev_match = h->prev_match.as<int>();
     SolveArgs sa;
     sa.partial = h->partial.as<double>();
     sa.blocks_per_pair = bpp;
@@ -510,7 +527,7 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
     for (int it = 0; it < h->prm.max_iterations; ++it) {
         {
             ProfScope prof(h, GICP_STAGE_OBJECTIVE, st);
-            objective_kernel<D, Real><<<ogrid, OBJ_THREADS, 0, st>>>(oa);
+            objective_kernel<D, Real><<<ogrid, OBJ_THREADS, OBJ_SMEM, st>>>(oa);
         }
         ProfScope prof(h, GICP_STAGE_SOLVE, st);
         if (sharded) {
@@ -558,7 +575,7 @@ int do_stage(gicpContext* h, const double* h_T, int* d_idx, double* d_dist, doub
     oa.out_W = d_W;
     oa.ignore_status = 1;
     // stage entry points always cover the whole source (no slicing), so their outputs are complete
-    objective_kernel<D, Real><<<dim3(bpp, np), OBJ_THREADS, 0, st>>>(oa);
+    objective_kernel<D, Real><<<dim3(bpp, np), OBJ_THREADS, OBJ_SMEM, st>>>(oa);
     h->launches += 1;
     if (h_out) {
         SolveArgs sa;
@@ -680,7 +697,7 @@ int gicpDestroy(gicpHandle h) {
     h->src.release();
     h->tgt.release();
     DevBuf* bufs[] = {&h->keys, &h->keys_alt, &h->vals, &h->vals_alt, &h->cub_tmp, &h->cell_count, &h->bbox_part,
-                      &h->knn_idx_tmp, &h->state, &h->partial, &h->red, &h->T_dev, &h->n_active};
+                      &h->knn_idx_tmp, &h->state, &h->partial, &h->red, &h->T_dev, &h->n_active, &h->prev_match};
     for (DevBuf* b : bufs) b->release();
     if (h->h_poll) cudaFreeHost(h->h_poll);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);

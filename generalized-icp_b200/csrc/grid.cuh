@@ -1,5 +1,5 @@
 // K1: uniform-grid build.  Replaces scipy's KDTree(points) (reference gicp.py:21,127).
-//   bbox -> per-cloud grid geometry -> cell key per point (+ histogram) -> radix sort by key
+//   bbox -> per-cloud grid geometry -> Morton cell key per point (+ histogram) -> radix sort by key
 //   -> exclusive scan of the histogram = cell_start -> gather points into sorted records.
 #pragma once
 #include "common.cuh"
@@ -73,37 +73,31 @@ __global__ void grid_meta_kernel(const double* __restrict__ part, int chunks, co
     for (int c = 0; c < 3; ++c) {
         if (c >= D || !(lo[c] <= hi[c])) { lo[c] = 0.0; hi[c] = 0.0; }
     }
+    // choose the cell edge: the Morton-padded table (2^(sum bits) entries) must fit the budget and
+    // no axis may need more than GICP_MAX_AXIS_BITS bits
+    CloudMeta m;
     double h = h_target;
-    int dims[3];
     for (int guard = 0; guard < 400; ++guard) {
-        long long total = 1;
+        m.h = h;
+        m.inv_h = 1.0 / h;
+        int sum_bits = 0;
+        bool ok = true;
         for (int c = 0; c < 3; ++c) {
-            double d = floor((hi[c] - lo[c]) / h) + 1.0;
-            d = fmin(d, 2.0e9);
-            dims[c] = (c < D) ? (int)d : 1;
-            total = (total > (long long)4e18 / dims[c]) ? (long long)4e18 : total * dims[c];
+            m.dims[c] = (c < D) ? cell_coord(hi[c], lo[c], m.inv_h) + 1 : 1;
+            int bts = 0;
+            while ((1 << bts) < m.dims[c] && bts < 31) ++bts;
+            m.bits[c] = bts;
+            sum_bits += bts;
+            if (bts > GICP_MAX_AXIS_BITS) ok = false;
         }
-        if (total <= budget) break;
+        if (ok && sum_bits <= 30 && (1LL << sum_bits) <= budget) break;
         h *= 1.2599210498948732;  // doubles the cell volume in 3-D
     }
-    CloudMeta m;
-    for (int c = 0; c < 3; ++c) { m.origin[c] = lo[c]; m.dims[c] = dims[c]; }
-    m.h = h;
-    m.inv_h = 1.0 / h;
+    for (int c = 0; c < 3; ++c) m.origin[c] = lo[c];
     m.cell_base = (int)((long long)cloud * budget);
     m.pt_begin = offsets[cloud];
     m.pt_end = offsets[cloud + 1];
-    // dims must reproduce what cell_coord() gives for the extreme points
-    for (int c = 0; c < D; ++c) m.dims[c] = cell_coord(hi[c], lo[c], m.inv_h) + 1;
-    {   // the recomputed dims can exceed the estimate by one cell through rounding: re-check
-        long long total = 1;
-        for (int c = 0; c < 3; ++c) total *= m.dims[c];
-        if (total > budget) {
-            m.h = h * 1.2599210498948732;
-            m.inv_h = 1.0 / m.h;
-            for (int c = 0; c < D; ++c) m.dims[c] = cell_coord(hi[c], lo[c], m.inv_h) + 1;
-        }
-    }
+    m.lut_base = cloud * 3 * GICP_LUT_N;
     meta[cloud] = m;
     if (bbox_out) {
         for (int c = 0; c < 3; ++c) { bbox_out[cloud * 6 + c] = lo[c]; bbox_out[cloud * 6 + 3 + c] = hi[c]; }
@@ -124,18 +118,22 @@ __global__ void __launch_bounds__(256) cell_key_kernel(const Real* __restrict__ 
         const int v = cell_coord((double)pts[(size_t)g * D + a], m.origin[a], m.inv_h);
         c[a] = min(max(v, 0), m.dims[a] - 1);
     }
-    const int cell = m.cell_base + (c[2] * m.dims[1] + c[1]) * m.dims[0] + c[0];
+    const int cell = m.cell_base + morton_code(c[0], c[1], c[2], m.bits[0], m.bits[1], m.bits[2]);
     keys[g] = (unsigned)cell;
     vals[g] = g;
     atomicAdd(&cell_count[cell], 1);
 }
 
-// grid (blocks, n_clouds): sorted position s -> record {coords, cloud-local index}; inverse permutation.
+// grid (blocks, n_clouds): sorted position s -> record {coords, idx}; idx is the cloud-local index of
+// the point in the caller's array (k-NN grids: it is the tie-break key and addresses the raw
+// coordinates) or, when `perm` is given (1-NN grids), the sorted position itself, with
+// perm[s] = cloud-local index kept on the side.  inv_perm[global row] = s.
 template <int D, typename Real>
 __global__ void __launch_bounds__(256) gather_sorted_kernel(const Real* __restrict__ pts,
                                                             const CloudMeta* __restrict__ meta,
                                                             const int* __restrict__ sorted_vals,
-                                                            PRec<Real>* __restrict__ spts, int* __restrict__ inv_perm) {
+                                                            PRec<Real>* __restrict__ spts, int* __restrict__ inv_perm,
+                                                            int* __restrict__ perm) {
     const CloudMeta m = meta[blockIdx.y];
     const int s = m.pt_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= m.pt_end) return;
@@ -144,9 +142,28 @@ __global__ void __launch_bounds__(256) gather_sorted_kernel(const Real* __restri
     r.x = pts[(size_t)g * D + 0];
     r.y = pts[(size_t)g * D + 1];
     r.z = (D == 3) ? pts[(size_t)g * D + (D - 1)] : Real(0);
-    r.idx = g - m.pt_begin;
+    r.idx = perm ? s : g - m.pt_begin;
     spts[s] = r;
     if (inv_perm) inv_perm[g] = s;
+    if (perm) perm[s] = g - m.pt_begin;
+}
+
+// grid (3 * GICP_LUT_N / 256, n_clouds): per-axis Morton spread tables, code(x,y,z) = lx[x] | ly[y] | lz[z]
+__global__ void morton_lut_kernel(const CloudMeta* __restrict__ meta, int* __restrict__ lut) {
+    const CloudMeta m = meta[blockIdx.y];
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 3 * GICP_LUT_N) return;
+    const int axis = e / GICP_LUT_N, v = e % GICP_LUT_N;
+    int code = 0, pos = 0;
+    for (int b = 0; b < GICP_MAX_AXIS_BITS; ++b) {
+        for (int ax = 0; ax < 3; ++ax) {
+            if (b < m.bits[ax]) {
+                if (ax == axis) code |= ((v >> b) & 1) << pos;
+                ++pos;
+            }
+        }
+    }
+    lut[m.lut_base + e] = code;
 }
 
 __global__ void offsets_to_int_kernel(const long long* __restrict__ in, int* __restrict__ out, int n) {

@@ -3,27 +3,32 @@
 // (reference gicp.py:19-35, 5-17): tree.query(k, distance_upper_bound) per point,
 // np.cov, np.linalg.eig, R diag(100,10) R^T.
 //
-// Work decomposition: one warp = 32 consecutive points of the cell-sorted order (so the
-// 32 queries sit in a handful of neighbouring cells).  The warp stages the candidate runs
-// of the cells around its queries' bounding box into shared memory with TMA bulk copies
-// (cp.async.bulk, one per grid row, completion on an mbarrier) and every lane scans the
-// staged candidates (broadcast LDS.128) keeping its own sorted top-k in registers.
-// Selection is exact: an fp32 distance is only a conservative filter; the key that is
-// ranked is the float64 squared distance (dx*dx + dy*dy) + dz*dz of the oracle, ties broken
-// by the lower point index.  The search grows ring by ring until every lane's k-th
-// distance is covered by the searched box (or the radius is).
+// Work decomposition: one warp = 32 consecutive points of the Morton-sorted order (a compact
+// blob of a few cells).  The warp stages the cell blocks around its queries with TMA bulk copies
+// (stream.cuh) and every lane scans the staged candidates (broadcast LDS.128) keeping its own
+// sorted top-k in registers.  Selection is exact: an fp32 distance is only a conservative
+// filter; the ranked key is the float64 squared distance (dx*dx + dy*dy) + dz*dz of the oracle,
+// ties broken by the lower point index.  Survivors of the filter are parked in a per-lane queue in
+// shared memory and merged into the sorted top-k in batches, so that the long unrolled insertion
+// network runs with many lanes active.  The search grows ring by ring (ring 0 = the queries' own
+// cells) until every lane's k-th distance is covered by the searched box (or the radius is).
 #pragma once
 #include "common.cuh"
+#include "stream.cuh"
 
 namespace gicp {
 
 constexpr int KNN_WARPS = 4;
 constexpr int KNN_THREADS = KNN_WARPS * 32;
 constexpr int KNN_STAGE_BYTES = 8192;  // per warp
+constexpr int KNN_QUEUE = 24;          // parked survivors per lane
+constexpr int KNN_WARP_SMEM = KNN_STAGE_BYTES + KNN_QUEUE * 32 * 12;
+constexpr int KNN_GROUP_REACH = 4;
 
 template <typename Real> struct KnnArgs {
     const CloudMeta* meta;
     const int* cell_start;
+    const int* lut;
     const PRec<Real>* spts;
     const Real* raw;     // caller's (n_total, D) array: neighbour coordinates for the covariance
     Real* cov_sorted;    // [n_total][NS], cell-sorted order
@@ -44,9 +49,14 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_cov_kernel(const KnnArgs<Real
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    PRec<Real>* stage = reinterpret_cast<PRec<Real>*>(smem_raw + 128 + warp * KNN_STAGE_BYTES);
-    uint64_t* bar = bars + warp;
-    constexpr int CAP = KNN_STAGE_BYTES / (int)sizeof(PRec<Real>);
+    unsigned char* wbase = smem_raw + 128 + warp * KNN_WARP_SMEM;
+    WarpStage<Real> ws;
+    ws.buf = reinterpret_cast<PRec<Real>*>(wbase);
+    ws.bar = bars + warp;
+    ws.phase = 0;
+    ws.cap = KNN_STAGE_BYTES / (int)sizeof(PRec<Real>);
+    double* qd = reinterpret_cast<double*>(wbase + KNN_STAGE_BYTES);             // [KNN_QUEUE][32]
+    int* qi = reinterpret_cast<int*>(wbase + KNN_STAGE_BYTES + KNN_QUEUE * 32 * 8);  // [KNN_QUEUE][32]
 
     const CloudMeta m = a.meta[blockIdx.y];
     int begin = m.pt_begin, end = m.pt_end;
@@ -54,20 +64,15 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_cov_kernel(const KnnArgs<Real
     const int base = begin + (blockIdx.x * KNN_WARPS + warp) * 32;
     if (base >= end) return;
 
-    if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    if (lane == 0) { mbar_init(ws.bar, 1); mbar_fence_init(); }
     __syncwarp();
-    uint32_t phase = 0;
 
     const bool valid = base + lane < end;
     const PRec<Real> me = a.spts[valid ? base + lane : end - 1];
     const int my_idx = (int)me.idx;
-    const int nx = m.dims[0], ny = m.dims[1], nz = m.dims[2];
-    int cx = min(max(cell_coord((double)me.x, m.origin[0], m.inv_h), 0), nx - 1);
-    int cy = min(max(cell_coord((double)me.y, m.origin[1], m.inv_h), 0), ny - 1);
-    int cz = (D == 3) ? min(max(cell_coord((double)me.z, m.origin[2], m.inv_h), 0), nz - 1) : 0;
-    const int xa = warp_min(cx), xb = warp_max(cx);
-    const int ya = warp_min(cy), yb = warp_max(cy);
-    const int za = warp_min(cz), zb = warp_max(cz);
+    const int cx = min(max(cell_coord((double)me.x, m.origin[0], m.inv_h), 0), m.dims[0] - 1);
+    const int cy = min(max(cell_coord((double)me.y, m.origin[1], m.inv_h), 0), m.dims[1] - 1);
+    const int cz = (D == 3) ? min(max(cell_coord((double)me.z, m.origin[2], m.inv_h), 0), m.dims[2] - 1) : 0;
 
     // sorted top-k: slots [KCAP-k, KCAP) are live, the ones before hold -1 sentinels
     double ad[KCAP];
@@ -81,91 +86,73 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_cov_kernel(const KnnArgs<Real
     }
     float thr32 = __double2float_ru(r2cap * (1.0 + 1e-6));
     const Real mx = me.x, my = me.y, mz = me.z;
+    int qn = 0;
 
-    const int rho_max = max(1, (int)ceil(a.radius / (m.h * (1.0 - 1e-9))));
-    for (int rho = 1; rho <= rho_max; ++rho) {
-        const int X0 = max(xa - rho, 0), X1 = min(xb + rho, nx - 1);
-        const int Y0 = max(ya - rho, 0), Y1 = min(yb + rho, ny - 1);
-        const int Z0 = max(za - rho, 0), Z1 = min(zb + rho, nz - 1);
-        const int PX0 = max(xa - rho + 1, 0), PX1 = min(xb + rho - 1, nx - 1);
-        const int PY0 = max(ya - rho + 1, 0), PY1 = min(yb + rho - 1, ny - 1);
-        const int PZ0 = max(za - rho + 1, 0), PZ1 = min(zb + rho - 1, nz - 1);
-        const int nyb = Y1 - Y0 + 1, nzb = Z1 - Z0 + 1;
-        const int n_slots = 2 * nyb * nzb;
-        const int n_sweeps = (rho == 1) ? 2 : 1;
-        for (int sweep = 0; sweep < n_sweeps; ++sweep) {
-            for (int g0 = 0; g0 < n_slots; g0 += 32) {
-                const int e = g0 + lane;
-                int start = 0, len = 0;
-                if (e < n_slots) {
-                    const int row = e >> 1, side = e & 1;
-                    const int y = Y0 + row % nyb, z = Z0 + row / nyb;
-                    int xlo = 0, xhi = -1;
-                    if (rho == 1) {
-                        const bool core = (y >= ya && y <= yb && z >= za && z <= zb);
-                        if (side == 0 && core == (sweep == 0)) { xlo = X0; xhi = X1; }
-                    } else {
-                        const bool in_prev = (y >= PY0 && y <= PY1 && z >= PZ0 && z <= PZ1);
-                        if (!in_prev) {
-                            if (side == 0) { xlo = X0; xhi = X1; }
-                        } else if (side == 0) { xlo = X0; xhi = PX0 - 1; }
-                        else { xlo = PX1 + 1; xhi = X1; }
-                    }
-                    if (xhi >= xlo) {
-                        const int rowbase = m.cell_base + (z * ny + y) * nx;
-                        start = __ldg(a.cell_start + rowbase + xlo);
-                        len = __ldg(a.cell_start + rowbase + xhi + 1) - start;
-                    }
-                }
-                const int incl = warp_incl_scan(len, lane);
-                const int excl = incl - len;
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                for (int w0 = 0; w0 < total; w0 += CAP) {
-                    const int n_win = min(CAP, total - w0);
-                    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(n_win * sizeof(PRec<Real>)));
-                    __syncwarp();
-                    const int lo = max(excl, w0), hi = min(excl + len, w0 + CAP);
-                    if (hi > lo)
-                        tma_load_1d(stage + (lo - w0), a.spts + start + (lo - excl),
-                                    (uint32_t)((hi - lo) * sizeof(PRec<Real>)), bar);
-                    mbar_wait(bar, phase);
-                    phase ^= 1u;
-                    for (int j = 0; j < n_win; ++j) {
-                        const PRec<Real> c = stage[j];
-                        bool pass;
-                        if (sizeof(Real) == 4) {
-                            const float dx = (float)c.x - (float)mx, dy = (float)c.y - (float)my,
-                                        dz = (float)c.z - (float)mz;
-                            pass = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr32;
-                        } else {
-                            pass = true;
-                        }
-                        if (pass) {
-                            const double e2 = exact_d2((double)c.x - (double)mx, (double)c.y - (double)my,
-                                                       (double)c.z - (double)mz);
-                            const int ci = (int)c.idx;
-                            bool lt_s = key_less(e2, ci, ad[KCAP - 1], ai[KCAP - 1]);
-                            if (lt_s) {
+    auto drain = [&]() {
+        const int nmax = warp_max(qn);
+        for (int i = 0; i < nmax; ++i) {
+            if (i < qn) {
+                const double e2 = qd[i * 32 + lane];
+                const int ci = qi[i * 32 + lane];
+                bool lt_s = key_less(e2, ci, ad[KCAP - 1], ai[KCAP - 1]);
+                if (lt_s) {
 #pragma unroll
-                                for (int s = KCAP - 1; s > 0; --s) {
-                                    const bool lt_prev = key_less(e2, ci, ad[s - 1], ai[s - 1]);
-                                    if (lt_prev) { ad[s] = ad[s - 1]; ai[s] = ai[s - 1]; }
-                                    else if (lt_s) { ad[s] = e2; ai[s] = ci; }
-                                    lt_s = lt_prev;
-                                }
-                                if (lt_s) { ad[0] = e2; ai[0] = ci; }
-                                thr32 = __double2float_ru(ad[KCAP - 1] * (1.0 + 1e-6));
-                            }
-                        }
+                    for (int s = KCAP - 1; s > 0; --s) {
+                        const bool lt_prev = key_less(e2, ci, ad[s - 1], ai[s - 1]);
+                        if (lt_prev) { ad[s] = ad[s - 1]; ai[s] = ai[s - 1]; }
+                        else if (lt_s) { ad[s] = e2; ai[s] = ci; }
+                        lt_s = lt_prev;
                     }
-                    __syncwarp();
+                    if (lt_s) { ad[0] = e2; ai[0] = ci; }
                 }
             }
         }
-        // done when the searched box covers every lane's k-th distance, or the radius
-        const double cover = rho * m.h * (1.0 - 1e-9);
-        const bool mine_done = (ai[KCAP - 1] != INT_MAX) && (ad[KCAP - 1] <= cover * cover);
-        if (__all_sync(0xffffffffu, mine_done) || cover >= a.radius) break;
+        qn = 0;
+        thr32 = __double2float_ru(ad[KCAP - 1] * (1.0 + 1e-6));
+    };
+
+    const int rho_max = max(1, (int)ceil(a.radius / (m.h * (1.0 - 1e-9))));
+    unsigned pending = 0xffffffffu;
+    while (pending) {
+        const unsigned grp = next_group(pending, cx, cy, cz, KNN_GROUP_REACH);
+        pending &= ~grp;
+        const bool mine = (grp >> lane) & 1u;
+        const int mycell[3] = {cx, cy, cz};
+        int qlo[3], qhi[3];
+        group_union(grp, lane, mycell, mycell, m, qlo, qhi);
+        int plo[3] = {0, 0, 0}, phi[3] = {-1, -1, -1};
+        for (int rho = 0; rho <= rho_max; ++rho) {
+            int lo[3], hi[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { lo[c] = max(qlo[c] - rho, 0); hi[c] = min(qhi[c] + rho, m.dims[c] - 1); }
+            stream_cells<Real>(m, a.cell_start, a.lut, a.spts, lo, hi, plo, phi, rho > 0, ws, lane,
+                               [&](const PRec<Real>& c) {
+                bool pass = mine;
+                if (sizeof(Real) == 4) {
+                    const float dx = (float)c.x - (float)mx, dy = (float)c.y - (float)my, dz = (float)c.z - (float)mz;
+                    pass = pass && (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr32);
+                }
+                if (pass) {
+                    const double e2 = exact_d2((double)c.x - (double)mx, (double)c.y - (double)my,
+                                               (double)c.z - (double)mz);
+                    const int ci = (int)c.idx;
+                    if (key_less(e2, ci, ad[KCAP - 1], ai[KCAP - 1])) {
+                        qd[qn * 32 + lane] = e2;
+                        qi[qn * 32 + lane] = ci;
+                        ++qn;
+                    }
+                }
+                if (__any_sync(0xffffffffu, qn == KNN_QUEUE)) drain();
+            });
+            drain();
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { plo[c] = lo[c]; phi[c] = hi[c]; }
+            if (rho == 0) continue;
+            // done when the searched box covers every lane's k-th distance, or the radius
+            const double cover = rho * m.h * (1.0 - 1e-9);
+            const bool mine_done = !mine || ((ai[KCAP - 1] != INT_MAX) && (ad[KCAP - 1] <= cover * cover));
+            if (__all_sync(0xffffffffu, mine_done) || cover >= a.radius) break;
+        }
     }
 
     if (!valid) return;

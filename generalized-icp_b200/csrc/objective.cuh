@@ -8,18 +8,23 @@
 //   sum e^T W e  gives the inner objective exactly; K4 then minimises it without touching the
 //   points again.
 //
-// One thread per source point (cell-sorted order, so a warp's queries hit neighbouring target
-// cells).  Exactness: an fp32 distance with a proven error margin filters candidates, the ranked
+// One thread per source point; a warp owns 32 consecutive points of the source's Morton order (a
+// compact blob), stages the target cells around the blob's image with TMA bulk copies
+// (stream.cuh) and every lane scans the staged candidates (broadcast LDS.128).
+// Exactness: an fp32 distance with a proven error margin filters candidates, the ranked
 // key is the float64 squared distance of the oracle, ties go to the lower target index.
 // Per-point algebra runs in fp64; products are accumulated per thread in the storage precision,
 // reduced with warp shuffles, then across warps and blocks in fp64 in a fixed order (bitwise
 // reproducible, no float atomics).
 #pragma once
 #include "common.cuh"
+#include "stream.cuh"
 
 namespace gicp {
 
 constexpr int OBJ_THREADS = 128;
+constexpr int OBJ_STAGE_BYTES = 8192;  // per warp
+constexpr int OBJ_GROUP_REACH = 4;
 
 template <typename Real> struct ObjArgs {
     const CloudMeta* src_meta;
@@ -27,8 +32,12 @@ template <typename Real> struct ObjArgs {
     const Real* src_cov;
     const CloudMeta* tgt_meta;
     const int* tgt_cell_start;
-    const PRec<Real>* tgt_spts;
+    const int* tgt_lut;
+    const PRec<Real>* tgt_spts;   // records carry their own sorted position in .idx
     const Real* tgt_cov;
+    const int* src_perm;          // sorted position -> cloud-local input index
+    const int* tgt_perm;
+    int* prev_match;              // optional [n_src_total], source nn order: last iteration's match (position) or -1
     const PairState* state;
     const double* T_override;  // optional [n_pairs][(D+1)^2], device
     double* partial;           // [n_pairs][blocks_per_pair][NRED]
@@ -72,10 +81,17 @@ __global__ void __launch_bounds__(OBJ_THREADS) objective_kernel(const ObjArgs<Re
     const CloudMeta mt = a.tgt_meta[pair];
     int begin = ms.pt_begin, end = ms.pt_end;
     if (a.slice_begin >= 0) { begin = max(begin, a.slice_begin); end = min(end, a.slice_end); }
-    const int nx = mt.dims[0], ny = mt.dims[1], nz = mt.dims[2];
-    const double cover1 = mt.h * (1.0 - 1e-9);
-    const int rho_max = max(1, (int)ceil(a.d_max / cover1));
     const double d2cap = a.d_max * a.d_max * (1.0 + 1e-9);
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpStage<Real> ws;
+    ws.buf = reinterpret_cast<PRec<Real>*>(smem_raw + 128 + warp * OBJ_STAGE_BYTES);
+    ws.bar = reinterpret_cast<uint64_t*>(smem_raw) + warp;
+    ws.phase = 0;
+    ws.cap = OBJ_STAGE_BYTES / (int)sizeof(PRec<Real>);
+    if (lane == 0) { mbar_init(ws.bar, 1); mbar_fence_init(); }
+    __syncwarp();
 
     AccT acc[NQ];
 #pragma unroll
@@ -84,9 +100,11 @@ __global__ void __launch_bounds__(OBJ_THREADS) objective_kernel(const ObjArgs<Re
     int cnt = 0;
 
     for (int it = 0; it < a.ppt; ++it) {
-        const int s = begin + (blockIdx.x * a.ppt + it) * OBJ_THREADS + threadIdx.x;
-        if (s >= end) break;
-        const PRec<Real> p = a.src_spts[s];
+        const int wbase = begin + (blockIdx.x * a.ppt + it) * OBJ_THREADS + warp * 32;
+        if (wbase >= end) break;  // warp-uniform
+        const int s = wbase + lane;
+        const bool valid = s < end;
+        const PRec<Real> p = a.src_spts[valid ? s : end - 1];
         double pp[3] = {0.0, 0.0, 0.0};  // p' = R p + t (gicp.py:119)
         {
             const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
@@ -98,58 +116,95 @@ __global__ void __launch_bounds__(OBJ_THREADS) objective_kernel(const ObjArgs<Re
             }
         }
         // ---- 1-NN in the target grid, bounded by d_max (exactly equivalent to the unbounded
-        //      query + gate of gicp.py:132-138, SURVEY appendix A rule 6) ----
-        const int cx = cell_coord(pp[0], mt.origin[0], mt.inv_h);
-        const int cy = cell_coord(pp[1], mt.origin[1], mt.inv_h);
-        const int cz = (D == 3) ? cell_coord(pp[2], mt.origin[2], mt.inv_h) : 0;
+        //      query + gate of gicp.py:132-138, SURVEY appendix A rule 6).  The match of the previous
+        //      outer iteration gives an upper bound on the new nearest distance, so only the cells
+        //      that intersect the ball of that radius around p' are searched (still exact). ----
         double bestd = d2cap;
-        int besti = INT_MAX, bestpos = -1;
+        int bestpos = -1;
+        if (a.prev_match) {
+            const int pm = a.prev_match[valid ? s : end - 1];
+            if (pm >= 0) {
+                const PRec<Real> qo = a.tgt_spts[pm];
+                const double e2 = exact_d2((double)qo.x - pp[0], (double)qo.y - pp[1], (double)qo.z - pp[2]);
+                if (e2 <= d2cap) { bestd = e2; bestpos = pm; }
+            }
+        }
         const float fx = (float)pp[0], fy = (float)pp[1], fz = (float)pp[2];
-        const double P = fmax(fabs(pp[0]), fmax(fabs(pp[1]), fabs(pp[2])));
-        float thr32 = __double2float_ru(bestd * (1.0 + 1e-6) + 4e-7 * sqrt(bestd) * P + 1e-30);
-        for (int rho = 1; rho <= rho_max; ++rho) {
-            const int y0 = max(cy - rho, 0), y1 = min(cy + rho, ny - 1);
-            const int z0 = (D == 3) ? max(cz - rho, 0) : 0, z1 = (D == 3) ? min(cz + rho, nz - 1) : 0;
+        const float Pf = fmaxf(fabsf(fx), fmaxf(fabsf(fy), fabsf(fz))) * 1.0000002f;
+        // conservative fp32 filter threshold: |d2_32 - d2| <= 2 sqrt(3) d u P + 6 u d2  (u = 2^-24)
+        const float c1 = 5e-7f * Pf * 1.0001f;
+        auto filter_thr = [&](double bd) {
+            const float b = __double2float_ru(bd);
+            return fmaf(b, 1.000002f, c1 * sqrtf(b)) + 1e-30f;
+        };
+        float thr32 = filter_thr(bestd);
+        auto test = [&](const PRec<Real>& c) {
+            bool pass = true;
+            if (sizeof(Real) == 4) {
+                const float dx = (float)c.x - fx, dy = (float)c.y - fy, dz = (float)c.z - fz;
+                pass = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr32;
+            }
+            if (pass) {
+                const double e2 = exact_d2((double)c.x - pp[0], (double)c.y - pp[1], (double)c.z - pp[2]);
+                const int cpos = (int)c.idx;
+                // exact ties (same float64 distance) go to the lower input index, like the oracle
+                if (e2 < bestd || (e2 == bestd && bestpos >= 0 && cpos != bestpos &&
+                                   a.tgt_perm[cpos] < a.tgt_perm[bestpos])) {
+                    bestd = e2; bestpos = cpos;
+                    thr32 = filter_thr(bestd);
+                }
+            }
+        };
+        const double rad = sqrt(bestd) * (1.0 + 1e-9) + 1e-300;
+        int mylo[3], myhi[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            mylo[i] = (i < D) ? cell_coord(pp[i] - rad, mt.origin[i], mt.inv_h) : 0;
+            myhi[i] = (i < D) ? cell_coord(pp[i] + rad, mt.origin[i], mt.inv_h) : 0;
+        }
+        const bool tracked = bestpos >= 0;
+        if (tracked) {
+            // ---- phase A: per-lane walk over the (few) cells that intersect the ball ----
+            const int* L = a.tgt_lut + mt.lut_base;
+            const int x0 = max(mylo[0], 0), x1 = min(myhi[0], mt.dims[0] - 1);
+            const int y0 = max(mylo[1], 0), y1 = min(myhi[1], mt.dims[1] - 1);
+            const int z0 = max(mylo[2], 0), z1 = min(myhi[2], mt.dims[2] - 1);
             for (int z = z0; z <= z1; ++z) {
+                const int lz = __ldg(L + 2 * GICP_LUT_N + z);
                 for (int y = y0; y <= y1; ++y) {
-                    const bool inner_row = (rho > 1) && (abs(y - cy) < rho) && (D == 2 || abs(z - cz) < rho);
-                    const int n_runs = inner_row ? 2 : 1;
-                    for (int run = 0; run < n_runs; ++run) {
-                        int xlo, xhi;
-                        if (!inner_row) { xlo = max(cx - rho, 0); xhi = min(cx + rho, nx - 1); }
-                        else if (run == 0) { xlo = xhi = cx - rho; if (xlo < 0 || xlo > nx - 1) continue; }
-                        else { xlo = xhi = cx + rho; if (xlo < 0 || xlo > nx - 1) continue; }
-                        if (xhi < xlo) continue;
-                        const int rowbase = mt.cell_base + (z * ny + y) * nx;
-                        const int j0 = __ldg(a.tgt_cell_start + rowbase + xlo);
-                        const int j1 = __ldg(a.tgt_cell_start + rowbase + xhi + 1);
-                        for (int j = j0; j < j1; ++j) {
-                            const PRec<Real> c = a.tgt_spts[j];
-                            bool pass = true;
-                            if (sizeof(Real) == 4) {
-                                const float dx = (float)c.x - fx, dy = (float)c.y - fy, dz = (float)c.z - fz;
-                                pass = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr32;
-                            }
-                            if (pass) {
-                                const double e2 = exact_d2((double)c.x - pp[0], (double)c.y - pp[1],
-                                                           (double)c.z - pp[2]);
-                                const int ci = (int)c.idx;
-                                if (e2 < bestd || (e2 == bestd && ci < besti)) {
-                                    bestd = e2; besti = ci; bestpos = j;
-                                    thr32 = __double2float_ru(bestd * (1.0 + 1e-6) + 4e-7 * sqrt(bestd) * P + 1e-30);
-                                }
-                            }
-                        }
+                    const int lyz = lz | __ldg(L + GICP_LUT_N + y);
+                    for (int x = x0; x <= x1; ++x) {
+                        const int* cs = a.tgt_cell_start + mt.cell_base + (lyz | __ldg(L + x));
+                        const int j0 = __ldg(cs), j1 = __ldg(cs + 1);
+                        for (int j = j0; j < j1; ++j) test(a.tgt_spts[j]);
                     }
                 }
             }
-            const double cover = rho * cover1;
-            if ((besti != INT_MAX && bestd <= cover * cover) || cover >= a.d_max) break;
         }
-        const double dist = (besti != INT_MAX) ? sqrt(bestd) : INFINITY;
-        const bool matched = (besti != INT_MAX) && !(dist > a.d_max);  // gicp.py:136 rejects d > d_max
-        const size_t out_row = (size_t)ms.pt_begin + (size_t)p.idx;
-        if (a.out_idx) a.out_idx[out_row] = matched ? besti : -1;
+        // ---- phase B: lanes without a usable previous match (first iteration, gated-out points):
+        //      warp-cooperative search of the whole d_max ball through the TMA stage ----
+        unsigned pending = __ballot_sync(0xffffffffu, !tracked);
+        if (pending) {
+            const int cx = cell_coord(pp[0], mt.origin[0], mt.inv_h);
+            const int cy = cell_coord(pp[1], mt.origin[1], mt.inv_h);
+            const int cz = (D == 3) ? cell_coord(pp[2], mt.origin[2], mt.inv_h) : 0;
+            const int none[3] = {0, 0, 0};
+            while (pending) {
+                const unsigned grp = next_group(pending, cx, cy, cz, OBJ_GROUP_REACH);
+                pending &= ~grp;
+                const bool mine = (grp >> lane) & 1u;
+                int lo[3], hi[3];
+                group_union(grp, lane, mylo, myhi, mt, lo, hi);
+                stream_cells<Real>(mt, a.tgt_cell_start, a.tgt_lut, a.tgt_spts, lo, hi, none, none, false, ws, lane,
+                                   [&](const PRec<Real>& c) { if (mine) test(c); });
+            }
+        }
+        if (!valid) continue;
+        const double dist = (bestpos >= 0) ? sqrt(bestd) : INFINITY;
+        const bool matched = (bestpos >= 0) && !(dist > a.d_max);  // gicp.py:136 rejects d > d_max
+        if (a.prev_match) a.prev_match[s] = matched ? bestpos : -1;
+        const size_t out_row = (size_t)ms.pt_begin + (size_t)a.src_perm[s];
+        if (a.out_idx) a.out_idx[out_row] = matched ? a.tgt_perm[bestpos] : -1;
         if (a.out_dist) a.out_dist[out_row] = dist;
         if (!matched) {
             if (a.out_W) {
@@ -237,7 +292,6 @@ __global__ void __launch_bounds__(OBJ_THREADS) objective_kernel(const ObjArgs<Re
 
     // ---- block reduction: warp shuffles, then the warps' sums in fixed order in fp64 ----
     __shared__ double s_red[OBJ_THREADS / 32][NQ + 2];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
     for (int i = 0; i < NQ; ++i) {
         const AccT r = warp_sum(acc[i]);
