@@ -126,7 +126,7 @@ struct gicpContext {
     gicpParams prm;
     CloudSet src, tgt;
     DevBuf keys, keys_alt, vals, vals_alt, cub_tmp, cell_count, bbox_part, knn_idx_tmp;
-    DevBuf state, partial, red, T_dev, n_active, prev_match;
+    DevBuf state, partial, red, T_dev, n_active, prev_match, ovf_count, ovf_list;
     int* h_poll = nullptr;  // pinned
     cudaEvent_t poll_event = nullptr;
     int64_t launches = 0;
@@ -324,20 +324,40 @@ int launch_knn(gicpContext* h, CloudSet& cs, int* d_idx, double* d_dist, cudaStr
     const int span = (slice_b >= 0) ? (slice_e - slice_b) : cs.max_n;
     if (span <= 0) return 0;
     const int bx = (span + KNN_THREADS - 1) / KNN_THREADS;
-    const size_t smem = 128 + (size_t)KNN_WARPS * KNN_WARP_SMEM;
     dim3 grid(bx, cs.n_clouds);
+    // fast path's overflow hand-over: worst case every warp
+    const long long n_chunks = (long long)bx * KNN_WARPS * cs.n_clouds;
+    CU(h->ovf_count.ensure(sizeof(int)));
+    CU(h->ovf_list.ensure((size_t)n_chunks * sizeof(int2)));
+    a.overflow_count = h->ovf_count.as<int>();
+    a.overflow_list = h->ovf_list.as<int2>();
+    a.overflow_cap = (int)std::min<long long>(n_chunks, INT_MAX);
+    const bool fast = a.k + 8 <= knn_list_cap<Real>();
+    const size_t smem_g = 128 + (size_t)KNN_WARPS * KNN_WARP_SMEM;
+    const size_t smem_h = 128 + (size_t)KNN_WARPS * KNN_HIST_WARP_SMEM;
     ProfScope prof(h, GICP_STAGE_KNN_COV, st);
-#define KNN_LAUNCH(KC)                                                                                       \
+#define KNN_LAUNCH(KC, GRID, FROM_LIST)                                                                      \
     do {                                                                                                     \
-        CU(cudaFuncSetAttribute(knn_cov_kernel<D, Real, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                (int)smem));                                                                 \
-        knn_cov_kernel<D, Real, KC><<<grid, KNN_THREADS, smem, st>>>(a);                                     \
+        CU(cudaFuncSetAttribute(knn_general_kernel<D, Real, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                (int)smem_g));                                                               \
+        knn_general_kernel<D, Real, KC><<<GRID, KNN_THREADS, smem_g, st>>>(a, FROM_LIST);                    \
     } while (0)
-    if (a.k <= 6) KNN_LAUNCH(6);
-    else if (a.k <= 20) KNN_LAUNCH(20);
-    else KNN_LAUNCH(32);
+    if (fast) {
+        CU(cudaMemsetAsync(h->ovf_count.p, 0, sizeof(int), st));
+        CU(cudaFuncSetAttribute(knn_hist_kernel<D, Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+        CU(cudaFuncSetAttribute(knn_hist_kernel<D, Real>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        knn_hist_kernel<D, Real><<<grid, KNN_THREADS, smem_h, st>>>(a);
+        const dim3 lgrid(296, 1);
+        if (a.k <= 6) KNN_LAUNCH(6, lgrid, 1);
+        else KNN_LAUNCH(20, lgrid, 1);
+        h->launches += 2;
+    } else {
+        if (a.k <= 6) KNN_LAUNCH(6, grid, 0);
+        else if (a.k <= 20) KNN_LAUNCH(20, grid, 0);
+        else KNN_LAUNCH(32, grid, 0);
+        h->launches += 1;
+    }
 #undef KNN_LAUNCH
-    h->launches += 1;
     CU(cudaGetLastError());
     return 0;
 }
@@ -348,7 +368,7 @@ constexpr size_t OBJ_SMEM = 128 + (size_t)(OBJ_THREADS / 32) * OBJ_STAGE_BYTES;
 double auto_knn_cell(const gicpContext* h) {
     const double r = h->prm.max_distance_nearest_neighbors;
     if (h->prm.knn_cell > 0) return std::max(h->prm.knn_cell, r / 8.0);
-    return 0.5 * r;
+    return 0.25 * r;   // 2x2x2 cell blocks of r/2; measured optimum on the bench workload is r/5 .. r/4
 }
 double auto_nn_cell(const gicpContext* h) {
     const double r = h->prm.max_distance_correspondence;
@@ -697,7 +717,7 @@ int gicpDestroy(gicpHandle h) {
     h->src.release();
     h->tgt.release();
     DevBuf* bufs[] = {&h->keys, &h->keys_alt, &h->vals, &h->vals_alt, &h->cub_tmp, &h->cell_count, &h->bbox_part,
-                      &h->knn_idx_tmp, &h->state, &h->partial, &h->red, &h->T_dev, &h->n_active, &h->prev_match};
+                      &h->knn_idx_tmp, &h->state, &h->partial, &h->red, &h->T_dev, &h->n_active, &h->prev_match, &h->ovf_count, &h->ovf_list};
     for (DevBuf* b : bufs) b->release();
     if (h->h_poll) cudaFreeHost(h->h_poll);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);

@@ -5,13 +5,20 @@
 //
 // Work decomposition: one warp = 32 consecutive points of the Morton-sorted order (a compact
 // blob of a few cells).  The warp stages the cell blocks around its queries with TMA bulk copies
-// (stream.cuh) and every lane scans the staged candidates (broadcast LDS.128) keeping its own
-// sorted top-k in registers.  Selection is exact: an fp32 distance is only a conservative
-// filter; the ranked key is the float64 squared distance (dx*dx + dy*dy) + dz*dz of the oracle,
-// ties broken by the lower point index.  Survivors of the filter are parked in a per-lane queue in
-// shared memory and merged into the sorted top-k in batches, so that the long unrolled insertion
-// network runs with many lanes active.  The search grows ring by ring (ring 0 = the queries' own
-// cells) until every lane's k-th distance is covered by the searched box (or the radius is).
+// (stream.cuh) and every lane scans the staged candidates (broadcast LDS.128).
+//
+// Fast path (knn_hist_kernel): three sweeps, no long selection network.
+//   1. ring by ring (ring 0 = the queries' own cells) every lane histograms the fp32 distance of
+//      each candidate into 64 distance bins (lane-private column in shared memory); after a ring
+//      the bin holding the k-th candidate bounds the lane's k-th neighbour distance, and the
+//      search stops once the searched box covers that bound for every lane;
+//   2. the box is streamed once more and each lane keeps the candidates under its bound (k plus
+//      the few that share the last bin) in a lane-private list;
+//   3. the list is ranked by counting.  The ranked key is the float64 squared distance
+//      (dx*dx + dy*dy) + dz*dz of the oracle, ties to the lower point index: fp32 keys decide every
+//      comparison that falls outside their rounding band, exact keys the rest.
+// General path (knn_general_kernel): exact sorted top-k in registers fed through a per-lane queue;
+// used when k is too large for the fast path's list and for the warps whose list overflowed.
 #pragma once
 #include "common.cuh"
 #include "stream.cuh"
@@ -20,10 +27,13 @@ namespace gicp {
 
 constexpr int KNN_WARPS = 4;
 constexpr int KNN_THREADS = KNN_WARPS * 32;
-constexpr int KNN_STAGE_BYTES = 8192;  // per warp
-constexpr int KNN_QUEUE = 24;          // parked survivors per lane
+constexpr int KNN_STAGE_BYTES = 8192;   // per warp
+constexpr int KNN_QUEUE = 24;           // general path: parked survivors per lane
 constexpr int KNN_WARP_SMEM = KNN_STAGE_BYTES + KNN_QUEUE * 32 * 12;
 constexpr int KNN_GROUP_REACH = 4;
+constexpr int KNN_BINS = 64;            // fast path: distance bins per lane (uint8 counters)
+constexpr int KNN_LIST_BYTES = 8192;    // fast path: lane-private candidate list, per warp
+constexpr int KNN_HIST_WARP_SMEM = KNN_STAGE_BYTES + KNN_BINS * 32 + KNN_LIST_BYTES;
 
 template <typename Real> struct KnnArgs {
     const CloudMeta* meta;
@@ -38,32 +48,296 @@ template <typename Real> struct KnnArgs {
     double radius;
     double lam_t, lam_n;
     int slice_begin, slice_end;  // sorted-position slice handled by this rank (<0: whole clouds)
+    int* overflow_count;         // fast path -> general path hand-over
+    int2* overflow_list;         // (cloud, chunk base)
+    int overflow_cap;
 };
+
+// fast path list capacity per lane: 32 (float keys) / 21 (double keys)
+template <typename Real> __host__ __device__ constexpr int knn_list_cap() { return KNN_LIST_BYTES / (32 * ((int)sizeof(Real) + 4)); }
 
 __device__ __forceinline__ bool key_less(double d, int i, double dd, int ii) {
     return d < dd || (d == dd && i < ii);
 }
 
-template <int D, typename Real, int KCAP>
-__global__ void __launch_bounds__(KNN_THREADS) knn_cov_kernel(const KnnArgs<Real> a) {
+// gicp.py:11-16 / SURVEY 8c: regularised covariance from the neighbourhood's scatter matrix
+// S (00 01 02 11 12 22, already divided by cnt-1).  C: D(D+1)/2 entries.
+template <int D>
+__device__ __forceinline__ void regularised_cov(const double S[6], bool ident, double lam_t, double lam_n, double* C) {
+    bool finite = true;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) finite = finite && isfinite(S[i]);
+    if (!finite) ident = true;  // gicp.py:31-32
+    if (!ident) {
+        if constexpr (D == 2) {
+            // eigenvector of the largest eigenvalue (gicp.py:14-16): C = lam_n I + (lam_t-lam_n) v v^T
+            const double phi = 0.5 * atan2(2.0 * S[1], S[0] - S[3]);
+            double sn, cs;
+            sincos(phi, &sn, &cs);
+            const double dl = lam_t - lam_n;
+            C[0] = lam_n + dl * cs * cs;
+            C[1] = dl * cs * sn;
+            C[2] = lam_n + dl * sn * sn;
+        } else {
+            // normal = eigenvector of the smallest eigenvalue: C = lam_t I - (lam_t-lam_n) n n^T
+            double n[3];
+            smallest_eigvec3(S[0], S[1], S[2], S[3], S[4], S[5], n);
+            const double dl = lam_t - lam_n;
+            C[0] = lam_t - dl * n[0] * n[0];
+            C[1] = -dl * n[0] * n[1];
+            C[2] = -dl * n[0] * n[2];
+            C[3] = lam_t - dl * n[1] * n[1];
+            C[4] = -dl * n[1] * n[2];
+            C[5] = lam_t - dl * n[2] * n[2];
+        }
+    } else {
+        if constexpr (D == 2) { C[0] = 1.0; C[1] = 0.0; C[2] = 1.0; }
+        else { C[0] = 1.0; C[1] = 0.0; C[2] = 0.0; C[3] = 1.0; C[4] = 0.0; C[5] = 1.0; }
+    }
+}
+
+// ================================================================================================
+// fast path
+// ================================================================================================
+template <int D, typename Real>
+__global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Real> a) {
+    using KeyT = Real;  // list key: the fp32 filter distance (float storage) / the exact key (double storage)
+    constexpr int CAP = knn_list_cap<Real>();
+    constexpr int NS = Dim<D>::NS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char* wbase = smem_raw + 128 + warp * KNN_WARP_SMEM;
+    unsigned char* wbase = smem_raw + 128 + warp * KNN_HIST_WARP_SMEM;
     WarpStage<Real> ws;
     ws.buf = reinterpret_cast<PRec<Real>*>(wbase);
     ws.bar = bars + warp;
     ws.phase = 0;
     ws.cap = KNN_STAGE_BYTES / (int)sizeof(PRec<Real>);
-    double* qd = reinterpret_cast<double*>(wbase + KNN_STAGE_BYTES);             // [KNN_QUEUE][32]
-    int* qi = reinterpret_cast<int*>(wbase + KNN_STAGE_BYTES + KNN_QUEUE * 32 * 8);  // [KNN_QUEUE][32]
+    unsigned char* hist = wbase + KNN_STAGE_BYTES;                                  // [KNN_BINS][32] uint8
+    KeyT* lk = reinterpret_cast<KeyT*>(wbase + KNN_STAGE_BYTES + KNN_BINS * 32);    // [CAP][32]
+    int* li = reinterpret_cast<int*>(wbase + KNN_STAGE_BYTES + KNN_BINS * 32 + CAP * 32 * sizeof(KeyT));  // [CAP][32]
 
-    const CloudMeta m = a.meta[blockIdx.y];
+    const int cloud = blockIdx.y;
+    const CloudMeta m = a.meta[cloud];
     int begin = m.pt_begin, end = m.pt_end;
     if (a.slice_begin >= 0) { begin = max(begin, a.slice_begin); end = min(end, a.slice_end); }
     const int base = begin + (blockIdx.x * KNN_WARPS + warp) * 32;
     if (base >= end) return;
+    if (lane == 0) { mbar_init(ws.bar, 1); mbar_fence_init(); }
+#pragma unroll
+    for (int b = 0; b < KNN_BINS; ++b) hist[b * 32 + lane] = 0;
+    __syncwarp();
 
+    const bool valid = base + lane < end;
+    const PRec<Real> me = a.spts[valid ? base + lane : end - 1];
+    const int my_idx = (int)me.idx;
+    const Real mx = me.x, my = me.y, mz = me.z;
+    const int cx = min(max(cell_coord((double)mx, m.origin[0], m.inv_h), 0), m.dims[0] - 1);
+    const int cy = min(max(cell_coord((double)my, m.origin[1], m.inv_h), 0), m.dims[1] - 1);
+    const int cz = (D == 3) ? min(max(cell_coord((double)mz, m.origin[2], m.inv_h), 0), m.dims[2] - 1) : 0;
+
+    const double r2cap = a.radius * a.radius * (1.0 + 1e-12);
+    const float r2cap32 = __double2float_ru(r2cap * (1.0 + 1e-6));
+    // logarithmic distance bins straight from the float bit pattern: 8 bins per octave of d^2 (3
+    // mantissa bits), the last bin holds the radius; everything closer than radius/16 shares bin 0
+    const int ubase = (int)(__float_as_uint(r2cap32) >> 20) - (KNN_BINS - 1);
+    const float pad = cell_box_pad(m);
+    const int rho_max = max(1, (int)ceil(a.radius / (m.h * (1.0 - 1e-9))));
+    float bound32 = r2cap32;   // squared-distance bound under which at least k candidates lie
+    bool overflow = false;
+    int mcount = 0;
+
+    // fp32 distance of a candidate (float storage), or the float image of the exact one (double storage)
+    auto dist32 = [&](const PRec<Real>& c) {
+        if (sizeof(Real) == 4) {
+            const float dx = (float)c.x - (float)mx, dy = (float)c.y - (float)my, dz = (float)c.z - (float)mz;
+            return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        } else {
+            return (float)exact_d2((double)c.x - (double)mx, (double)c.y - (double)my, (double)c.z - (double)mz);
+        }
+    };
+
+    unsigned pending = 0xffffffffu;
+    while (pending) {
+        const unsigned grp = next_group(pending, cx, cy, cz, KNN_GROUP_REACH);
+        pending &= ~grp;
+        const bool mine = (grp >> lane) & 1u;
+        const int mycell[3] = {cx, cy, cz};
+        int qlo[3], qhi[3];
+        group_union(grp, lane, mycell, mycell, m, qlo, qhi);
+        int plo[3] = {0, 0, 0}, phi[3] = {-1, -1, -1};
+        int lo[3] = {0, 0, 0}, hi[3] = {-1, -1, -1};
+        // ---- sweep 1: histogram the distances ring by ring ----
+        for (int rho = 0; rho <= rho_max; ++rho) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { lo[c] = max(qlo[c] - rho, 0); hi[c] = min(qhi[c] + rho, m.dims[c] - 1); }
+            stream_cells<Real>(m, a.cell_start, a.lut, a.spts, lo, hi, plo, phi, rho > 0, ws, lane,
+                               [&](const PRec<Real>* w, int n) {
+                int j = 0;
+                for (; j + 4 <= n; j += 4) {     // 4 candidates in flight: the histogram update is a dependent chain
+                    const PRec<Real> c0 = w[j], c1 = w[j + 1], c2 = w[j + 2], c3 = w[j + 3];
+                    const float e0 = dist32(c0), e1 = dist32(c1), e2 = dist32(c2), e3 = dist32(c3);
+                    const int g0 = min(max((int)(__float_as_uint(e0) >> 20) - ubase, 0), KNN_BINS - 1);
+                    const int g1 = min(max((int)(__float_as_uint(e1) >> 20) - ubase, 0), KNN_BINS - 1);
+                    const int g2 = min(max((int)(__float_as_uint(e2) >> 20) - ubase, 0), KNN_BINS - 1);
+                    const int g3 = min(max((int)(__float_as_uint(e3) >> 20) - ubase, 0), KNN_BINS - 1);
+                    if (mine && e0 <= r2cap32) hist[g0 * 32 + lane] += 1;
+                    if (mine && e1 <= r2cap32) hist[g1 * 32 + lane] += 1;
+                    if (mine && e2 <= r2cap32) hist[g2 * 32 + lane] += 1;
+                    if (mine && e3 <= r2cap32) hist[g3 * 32 + lane] += 1;
+                }
+                for (; j < n; ++j) {
+                    const float e0 = dist32(w[j]);
+                    const int g0 = min(max((int)(__float_as_uint(e0) >> 20) - ubase, 0), KNN_BINS - 1);
+                    if (mine && e0 <= r2cap32) hist[g0 * 32 + lane] += 1;
+                }
+            });
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { plo[c] = lo[c]; phi[c] = hi[c]; }
+            if (rho == 0) continue;
+            // bin that holds the k-th candidate -> bound on the k-th neighbour distance.  (A counter
+            // that wrapped at 256 only makes the bound larger, never wrong.)
+            int cum = 0, kb = KNN_BINS;
+            for (int b = 0; b < KNN_BINS; ++b) {
+                cum += hist[b * 32 + lane];
+                if (cum >= a.k) { kb = b; break; }
+            }
+            // every candidate of bins <= kb has d2 < edge2 (exact: bin edges are float bit patterns)
+            const bool have = kb < KNN_BINS - 1;
+            const float edge2 = have ? __uint_as_float((unsigned)(ubase + kb + 1) << 20) : r2cap32;
+            const double cover = rho * m.h * (1.0 - 1e-9);
+            const bool mine_done = !mine || (have && (double)edge2 <= cover * cover);
+            if (__all_sync(0xffffffffu, mine_done) || cover >= a.radius) {
+                if (mine) bound32 = fminf(edge2, r2cap32);
+                break;
+            }
+        }
+        __syncwarp();
+        // ---- sweep 2: keep the candidates under the bound ----
+        const int none[3] = {0, 0, 0};
+        int cnt_l = 0;
+        stream_cells<Real>(m, a.cell_start, a.lut, a.spts, lo, hi, none, none, false, ws, lane,
+                           [&](const PRec<Real>* w, int n) {
+            for (int j = 0; j < n; ++j) {
+                const PRec<Real> c = w[j];
+                KeyT key;
+                if (sizeof(Real) == 4) key = (KeyT)dist32(c);
+                else key = (KeyT)exact_d2((double)c.x - (double)mx, (double)c.y - (double)my, (double)c.z - (double)mz);
+                if (mine && (float)key <= bound32) {
+                    if (cnt_l < CAP) { lk[cnt_l * 32 + lane] = key; li[cnt_l * 32 + lane] = (int)c.idx; }
+                    ++cnt_l;
+                }
+            }
+        }, [&](int x0, int y0, int z0, int x1, int y1, int z1) {
+            // only blocks that reach into some lane's ball are staged
+            return mine && cell_box_dist2(m, pad, (float)mx, (float)my, (float)mz, x0, y0, z0, x1, y1, z1) <= bound32;
+        });
+        if (mine) { mcount = min(cnt_l, CAP); overflow = cnt_l > CAP; }
+        __syncwarp();
+    }
+    // hand the whole warp to the general path if any lane's list overflowed
+    if (__any_sync(0xffffffffu, overflow)) {
+        if (lane == 0) {
+            const int slot = atomicAdd(a.overflow_count, 1);
+            if (slot < a.overflow_cap) a.overflow_list[slot] = make_int2(cloud, base);
+        }
+        return;
+    }
+    if (!valid) return;
+
+    // ---- sweep 3: rank the list by counting; winners (rank < k) go to their sorted slot ----
+    const size_t cloud_row0 = (size_t)m.pt_begin;
+    auto exact_key = [&](int idx) {
+        const Real* q = a.raw + (cloud_row0 + idx) * D;
+        const double dz = (D == 3) ? (double)q[D - 1] - (double)mz : 0.0;
+        return exact_d2((double)q[0] - (double)mx, (double)q[1] - (double)my, dz);
+    };
+    int n_valid = 0;            // neighbours that pass the exact radius test
+    double mean[3] = {0.0, 0.0, 0.0};
+    double S[6] = {0, 0, 0, 0, 0, 0};
+    int* out_idx = a.knn_idx ? a.knn_idx + (cloud_row0 + my_idx) * (size_t)a.k : nullptr;
+    double* out_d = a.knn_dist ? a.knn_dist + (cloud_row0 + my_idx) * (size_t)a.k : nullptr;
+    for (int i = 0; i < mcount; ++i) {
+        const KeyT ki = lk[i * 32 + lane];
+        const int ii = li[i * 32 + lane];
+        int r = 0;
+        if (sizeof(Real) == 4) {
+            const float lo_k = (float)ki * 0.999999f, hi_k = (float)ki * 1.000001f;
+            int below = 0, upto = 0;
+            for (int j = 0; j < mcount; ++j) {
+                const float kj = (float)lk[j * 32 + lane];
+                below += (kj < lo_k) ? 1 : 0;
+                upto += (kj <= hi_k) ? 1 : 0;
+            }
+            r = below;
+            if (upto - below > 1) {   // another candidate inside the fp32 rounding band: exact keys decide
+                const double ei = exact_key(ii);
+                for (int j = 0; j < mcount; ++j) {
+                    const float kj = (float)lk[j * 32 + lane];
+                    if (j != i && kj >= lo_k && kj <= hi_k) {
+                        const int ij = li[j * 32 + lane];
+                        r += key_less(exact_key(ij), ij, ei, ii) ? 1 : 0;
+                    }
+                }
+            }
+        } else {
+            for (int j = 0; j < mcount; ++j) r += key_less((double)lk[j * 32 + lane], li[j * 32 + lane], (double)ki, ii) ? 1 : 0;
+        }
+        if (r < a.k) {
+            const Real* q = a.raw + (cloud_row0 + ii) * D;
+            const double d0 = (double)q[0] - (double)mx, d1 = (double)q[1] - (double)my;
+            const double d2 = (D == 3) ? (double)q[D - 1] - (double)mz : 0.0;
+            const double dist = sqrt(exact_d2(d0, d1, d2));
+            const bool ok = dist < a.radius;         // exclusive bound, gicp.py:24
+            if (ok) {
+                ++n_valid;
+                // moments about the query point keep the scatter matrix accurate
+                mean[0] += d0; mean[1] += d1; mean[2] += d2;
+                S[0] += d0 * d0; S[1] += d0 * d1; S[2] += d0 * d2;
+                S[3] += d1 * d1; S[4] += d1 * d2; S[5] += d2 * d2;
+            }
+            if (out_idx) {
+                out_idx[r] = ok ? ii : -1;
+                if (out_d) out_d[r] = ok ? dist : INFINITY;
+            }
+        }
+    }
+    if (out_idx) {
+        for (int o = min(mcount, a.k); o < a.k; ++o) {
+            out_idx[o] = -1;
+            if (out_d) out_d[o] = INFINITY;
+        }
+    }
+    double C[NS];
+    const bool ident = n_valid <= 1;     // gicp.py:27,33-34
+    if (!ident) {
+        const double inv = 1.0 / n_valid;
+        const double m0 = mean[0] * inv, m1 = mean[1] * inv, m2 = mean[2] * inv;
+        const double f = 1.0 / (n_valid - 1);   // ddof = 1 (np.cov default, gicp.py:12)
+        S[0] = (S[0] - n_valid * m0 * m0) * f; S[1] = (S[1] - n_valid * m0 * m1) * f;
+        S[2] = (S[2] - n_valid * m0 * m2) * f; S[3] = (S[3] - n_valid * m1 * m1) * f;
+        S[4] = (S[4] - n_valid * m1 * m2) * f; S[5] = (S[5] - n_valid * m2 * m2) * f;
+    }
+    regularised_cov<D>(S, ident, a.lam_t, a.lam_n, C);
+    Real* out = a.cov_sorted + (size_t)(base + lane) * NS;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) out[i] = (Real)C[i];
+}
+
+// ================================================================================================
+// general path
+// ================================================================================================
+template <int D, typename Real, int KCAP>
+__device__ __forceinline__ void knn_general_chunk(const KnnArgs<Real>& a, int cloud, int base, int end,
+                                                  unsigned char* wbase, uint64_t* bar, int lane) {
+    WarpStage<Real> ws;
+    ws.buf = reinterpret_cast<PRec<Real>*>(wbase);
+    ws.bar = bar;
+    ws.phase = 0;
+    ws.cap = KNN_STAGE_BYTES / (int)sizeof(PRec<Real>);
+    double* qd = reinterpret_cast<double*>(wbase + KNN_STAGE_BYTES);                 // [KNN_QUEUE][32]
+    int* qi = reinterpret_cast<int*>(wbase + KNN_STAGE_BYTES + KNN_QUEUE * 32 * 8);  // [KNN_QUEUE][32]
+    const CloudMeta m = a.meta[cloud];
     if (lane == 0) { mbar_init(ws.bar, 1); mbar_fence_init(); }
     __syncwarp();
 
@@ -126,23 +400,26 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_cov_kernel(const KnnArgs<Real
 #pragma unroll
             for (int c = 0; c < 3; ++c) { lo[c] = max(qlo[c] - rho, 0); hi[c] = min(qhi[c] + rho, m.dims[c] - 1); }
             stream_cells<Real>(m, a.cell_start, a.lut, a.spts, lo, hi, plo, phi, rho > 0, ws, lane,
-                               [&](const PRec<Real>& c) {
-                bool pass = mine;
-                if (sizeof(Real) == 4) {
-                    const float dx = (float)c.x - (float)mx, dy = (float)c.y - (float)my, dz = (float)c.z - (float)mz;
-                    pass = pass && (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr32);
-                }
-                if (pass) {
-                    const double e2 = exact_d2((double)c.x - (double)mx, (double)c.y - (double)my,
-                                               (double)c.z - (double)mz);
-                    const int ci = (int)c.idx;
-                    if (key_less(e2, ci, ad[KCAP - 1], ai[KCAP - 1])) {
-                        qd[qn * 32 + lane] = e2;
-                        qi[qn * 32 + lane] = ci;
-                        ++qn;
+                               [&](const PRec<Real>* w, int n) {
+                for (int j = 0; j < n; ++j) {
+                    const PRec<Real> c = w[j];
+                    bool pass = mine;
+                    if (sizeof(Real) == 4) {
+                        const float dx = (float)c.x - (float)mx, dy = (float)c.y - (float)my, dz = (float)c.z - (float)mz;
+                        pass = pass && (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr32);
                     }
+                    if (pass) {
+                        const double e2 = exact_d2((double)c.x - (double)mx, (double)c.y - (double)my,
+                                                   (double)c.z - (double)mz);
+                        const int ci = (int)c.idx;
+                        if (key_less(e2, ci, ad[KCAP - 1], ai[KCAP - 1])) {
+                            qd[qn * 32 + lane] = e2;
+                            qi[qn * 32 + lane] = ci;
+                            ++qn;
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, qn == KNN_QUEUE)) drain();
                 }
-                if (__any_sync(0xffffffffu, qn == KNN_QUEUE)) drain();
             });
             drain();
 #pragma unroll
@@ -243,6 +520,34 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_cov_kernel(const KnnArgs<Real
     Real* out = a.cov_sorted + (size_t)(base + lane) * NS;
 #pragma unroll
     for (int i = 0; i < NS; ++i) out[i] = (Real)C[i];
+}
+
+// from_list = 0: grid (blocks, n_clouds), one warp per 32 sorted points.
+// from_list = 1: grid-stride over the fast path's overflow list.
+template <int D, typename Real, int KCAP>
+__global__ void __launch_bounds__(KNN_THREADS) knn_general_kernel(const KnnArgs<Real> a, int from_list) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* wbase = smem_raw + 128 + warp * KNN_WARP_SMEM;
+    if (!from_list) {
+        const CloudMeta m = a.meta[blockIdx.y];
+        int begin = m.pt_begin, end = m.pt_end;
+        if (a.slice_begin >= 0) { begin = max(begin, a.slice_begin); end = min(end, a.slice_end); }
+        const int base = begin + (blockIdx.x * KNN_WARPS + warp) * 32;
+        if (base >= end) return;
+        knn_general_chunk<D, Real, KCAP>(a, blockIdx.y, base, end, wbase, bars + warp, lane);
+    } else {
+        const int n = min(*a.overflow_count, a.overflow_cap);
+        for (int e = blockIdx.x * KNN_WARPS + warp; e < n; e += gridDim.x * KNN_WARPS) {
+            const int2 it = a.overflow_list[e];
+            const CloudMeta m = a.meta[it.x];
+            int end = m.pt_end;
+            if (a.slice_begin >= 0) end = min(end, a.slice_end);
+            knn_general_chunk<D, Real, KCAP>(a, it.x, it.y, end, wbase, bars + warp, lane);
+            __syncwarp();
+        }
+    }
 }
 
 }  // namespace gicp

@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(OBJ_THREADS) objective_kernel(const ObjArgs<Re
     int begin = ms.pt_begin, end = ms.pt_end;
     if (a.slice_begin >= 0) { begin = max(begin, a.slice_begin); end = min(end, a.slice_end); }
     const double d2cap = a.d_max * a.d_max * (1.0 + 1e-9);
+    const float pad = cell_box_pad(mt);
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -196,7 +197,15 @@ __global__ void __launch_bounds__(OBJ_THREADS) objective_kernel(const ObjArgs<Re
                 int lo[3], hi[3];
                 group_union(grp, lane, mylo, myhi, mt, lo, hi);
                 stream_cells<Real>(mt, a.tgt_cell_start, a.tgt_lut, a.tgt_spts, lo, hi, none, none, false, ws, lane,
-                                   [&](const PRec<Real>& c) { if (mine) test(c); });
+                                   [&](const PRec<Real>* w, int n) {
+                    for (int j = 0; j < n; ++j) {
+                        const PRec<Real> c = w[j];
+                        if (mine) test(c);
+                    }
+                }, [&](int x0, int y0, int z0, int x1, int y1, int z1) {
+                    // only blocks that reach into some lane's current best-distance ball are staged
+                    return mine && cell_box_dist2(mt, pad, fx, fy, fz, x0, y0, z0, x1, y1, z1) <= thr32;
+                });
             }
         }
         if (!valid) continue;

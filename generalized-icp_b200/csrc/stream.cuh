@@ -9,6 +9,8 @@
 // copies (cp.async.bulk, completion on the warp's mbarrier) and calls the consumer once per
 // staged candidate on all lanes (the candidate is a broadcast LDS.128).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace gicp {
@@ -20,15 +22,20 @@ template <typename Real> struct WarpStage {
     int cap;
 };
 
+struct NeedAll {};   // tag: no per-block culling
+
 // Streams every aligned cell block intersecting the cell box [lo, hi] (already clamped to the grid,
 // extent <= 64 cells per axis) - except the blocks that already intersected [plo, phi] when
-// has_prev - through the stage and calls consume(candidate) warp-synchronously.
-// All 32 lanes must call this together with identical boxes.
-template <typename Real, typename F>
+// has_prev - through the stage and hands each staged window to consume(records, count)
+// warp-synchronously (records are read as broadcast LDS.128).
+// need(x0, y0, z0, x1, y1, z1): optional per-lane predicate on a block's cell range; a non-empty
+// block that no lane needs is not staged.  All 32 lanes must call this together with identical boxes.
+template <typename Real, typename F, typename Need = NeedAll>
 __device__ __forceinline__ void stream_cells(const CloudMeta& m, const int* __restrict__ cell_start,
                                              const int* __restrict__ lut, const PRec<Real>* __restrict__ spts,
                                              const int lo[3], const int hi[3], const int plo[3], const int phi[3],
-                                             bool has_prev, WarpStage<Real>& ws, int lane, F&& consume) {
+                                             bool has_prev, WarpStage<Real>& ws, int lane, F&& consume,
+                                             Need need = Need()) {
     if (hi[0] < lo[0] || hi[1] < lo[1] || hi[2] < lo[2]) return;
     // block = 2 cells along every axis that has at least one Morton bit
     const int s0 = m.bits[0] > 0, s1 = m.bits[1] > 0, s2 = m.bits[2] > 0;
@@ -61,6 +68,20 @@ __device__ __forceinline__ void stream_cells(const CloudMeta& m, const int* __re
             start = __ldg(cs);
             len = __ldg(cs + cells_per_block) - start;
         }
+        if constexpr (!std::is_same<Need, NeedAll>::value) {
+            // cull: every lane tests every non-empty block of this round against its own ball
+            unsigned nonempty = __ballot_sync(0xffffffffu, len > 0);
+            unsigned keep = 0;
+            while (nonempty) {
+                const int src = __ffs(nonempty) - 1;
+                nonempty &= nonempty - 1;
+                const int bx = (b0 + __shfl_sync(0xffffffffu, ix, src)) << s0;
+                const int by = (b1 + __shfl_sync(0xffffffffu, iy, src)) << s1;
+                const int bz = (b2 + __shfl_sync(0xffffffffu, iz, src)) << s2;
+                if (__any_sync(0xffffffffu, need(bx, by, bz, bx + s0, by + s1, bz + s2))) keep |= 1u << src;
+            }
+            if (!((keep >> lane) & 1u)) len = 0;
+        }
         const int incl = warp_incl_scan(len, lane);
         const int excl = incl - len;
         const int total = __shfl_sync(0xffffffffu, incl, 31);
@@ -74,10 +95,34 @@ __device__ __forceinline__ void stream_cells(const CloudMeta& m, const int* __re
                             ws.bar);
             mbar_wait(ws.bar, ws.phase);
             ws.phase ^= 1u;
-            for (int j = 0; j < n_win; ++j) consume(ws.buf[j]);
+            consume(ws.buf, n_win);
             __syncwarp();
         }
     }
+}
+
+// fp32 rounding slack of the cell boxes below: cell membership is decided in double, the box is
+// rebuilt in float, so it is widened by a few ulps of the largest coordinate of the grid
+__device__ __forceinline__ float cell_box_pad(const CloudMeta& m) {
+    float c = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        c = fmaxf(c, fmaxf(fabsf((float)m.origin[a]), fabsf((float)(m.origin[a] + m.dims[a] * m.h))));
+    return 4e-6f * c + 1e-6f * (float)m.h;
+}
+
+// lower bound on the squared distance from a point to the box of cells [x0..x1] x [y0..y1] x [z0..z1]
+__device__ __forceinline__ float cell_box_dist2(const CloudMeta& m, float pad, float px, float py, float pz, int x0,
+                                                int y0, int z0, int x1, int y1, int z1) {
+    const float h = (float)m.h;
+    const float ox = (float)m.origin[0], oy = (float)m.origin[1], oz = (float)m.origin[2];
+    const float lx = ox + x0 * h - pad, hx = ox + (x1 + 1) * h + pad;
+    const float ly = oy + y0 * h - pad, hy = oy + (y1 + 1) * h + pad;
+    const float lz = oz + z0 * h - pad, hz = oz + (z1 + 1) * h + pad;
+    const float dx = fmaxf(0.f, fmaxf(lx - px, px - hx));
+    const float dy = fmaxf(0.f, fmaxf(ly - py, py - hy));
+    const float dz = fmaxf(0.f, fmaxf(lz - pz, pz - hz));
+    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
 }
 
 // Greedy spatial grouping of a warp's queries: returns the mask of still-pending lanes whose cell

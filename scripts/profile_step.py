@@ -15,7 +15,7 @@ cfg = {k: v for k, v in synthetic.CONFIG4.items() if k != "n"}
 src, tgt, off, _ = synthetic.patches3d_batch_device(pairs, n=points, seed=0, device="cuda", **cfg)
 off = off.cpu().numpy()
 eng = GicpEngine(3, "f32")
-eng.set_params(**synthetic.CONFIG4_PARAMS)
+eng.set_params(**synthetic.CONFIG4_PARAMS, knn_cell=float(os.environ.get("KNN_CELL", 0)), nn_cell=float(os.environ.get("NN_CELL", 0)))
 for _ in range(steps):
     eng.set_target(tgt, off)
     eng.set_source(src, off)
