@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -346,7 +347,15 @@ int launch_knn(gicpContext* h, CloudSet& cs, int* d_idx, double* d_dist, cudaStr
         CU(cudaMemsetAsync(h->ovf_count.p, 0, sizeof(int), st));
         CU(cudaFuncSetAttribute(knn_hist_kernel<D, Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
         CU(cudaFuncSetAttribute(knn_hist_kernel<D, Real>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        knn_hist_kernel<D, Real><<<grid, KNN_THREADS, smem_h, st>>>(a);
+        const size_t smem_l = (size_t)KNN_WARPS * KNN_LANE_WARP_SMEM;
+        const bool per_lane = getenv("GICP_KNN_COOP") ? atoi(getenv("GICP_KNN_COOP")) == 0 : true;
+        if (per_lane) {
+            CU(cudaFuncSetAttribute(knn_lane_kernel<D, Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+            CU(cudaFuncSetAttribute(knn_lane_kernel<D, Real>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            knn_lane_kernel<D, Real><<<grid, KNN_THREADS, smem_l, st>>>(a);
+        } else {
+            knn_hist_kernel<D, Real><<<grid, KNN_THREADS, smem_h, st>>>(a);
+        }
         const dim3 lgrid(296, 1);
         if (a.k <= 6) KNN_LAUNCH(6, lgrid, 1);
         else KNN_LAUNCH(20, lgrid, 1);
@@ -469,6 +478,8 @@ int objective_args(gicpContext* h, ObjArgs<Real>& a, int& blocks_per_pair, bool 
     a.out_W = nullptr;
     a.slice_begin = a.slice_end = -1;
     a.ignore_status = 0;
+    a.track_max_cells = getenv("GICP_TRACK_CELLS") ? atoi(getenv("GICP_TRACK_CELLS")) : 1 << 30;
+    a.centre_first = getenv("GICP_CENTRE_FIRST") ? atoi(getenv("GICP_CENTRE_FIRST")) : 1;
     int span = S.max_n;
     if (allow_slice && h->comm && S.n_clouds == 1) {
         a.slice_begin = (int)(S.n_total * h->rank / h->n_ranks);

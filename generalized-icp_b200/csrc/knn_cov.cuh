@@ -96,6 +96,94 @@ __device__ __forceinline__ void regularised_cov(const double S[6], bool ident, d
     }
 }
 
+// sweep 3 of the fast paths: rank a lane's candidate list by counting, accumulate the moments of the
+// winners (rank < k, inside the radius), write the optional index/distance outputs and the
+// regularised covariance of sorted position s.
+template <int D, typename Real>
+__device__ __forceinline__ void knn_rank_and_finish(const KnnArgs<Real>& a, const CloudMeta& m, int s, int my_idx,
+                                                    Real mx, Real my, Real mz, const Real* lk, const int* li,
+                                                    int lane, int mcount) {
+    using KeyT = Real;
+    constexpr int NS = Dim<D>::NS;
+    // ---- sweep 3: rank the list by counting; winners (rank < k) go to their sorted slot ----
+    const size_t cloud_row0 = (size_t)m.pt_begin;
+    auto exact_key = [&](int idx) {
+        const Real* q = a.raw + (cloud_row0 + idx) * D;
+        const double dz = (D == 3) ? (double)q[D - 1] - (double)mz : 0.0;
+        return exact_d2((double)q[0] - (double)mx, (double)q[1] - (double)my, dz);
+    };
+    int n_valid = 0;            // neighbours that pass the exact radius test
+    double mean[3] = {0.0, 0.0, 0.0};
+    double S[6] = {0, 0, 0, 0, 0, 0};
+    int* out_idx = a.knn_idx ? a.knn_idx + (cloud_row0 + my_idx) * (size_t)a.k : nullptr;
+    double* out_d = a.knn_dist ? a.knn_dist + (cloud_row0 + my_idx) * (size_t)a.k : nullptr;
+    for (int i = 0; i < mcount; ++i) {
+        const KeyT ki = lk[i * 32 + lane];
+        const int ii = li[i * 32 + lane];
+        int r = 0;
+        if (sizeof(Real) == 4) {
+            const float lo_k = (float)ki * 0.999999f, hi_k = (float)ki * 1.000001f;
+            int below = 0, upto = 0;
+            for (int j = 0; j < mcount; ++j) {
+                const float kj = (float)lk[j * 32 + lane];
+                below += (kj < lo_k) ? 1 : 0;
+                upto += (kj <= hi_k) ? 1 : 0;
+            }
+            r = below;
+            if (upto - below > 1) {   // another candidate inside the fp32 rounding band: exact keys decide
+                const double ei = exact_key(ii);
+                for (int j = 0; j < mcount; ++j) {
+                    const float kj = (float)lk[j * 32 + lane];
+                    if (j != i && kj >= lo_k && kj <= hi_k) {
+                        const int ij = li[j * 32 + lane];
+                        r += key_less(exact_key(ij), ij, ei, ii) ? 1 : 0;
+                    }
+                }
+            }
+        } else {
+            for (int j = 0; j < mcount; ++j) r += key_less((double)lk[j * 32 + lane], li[j * 32 + lane], (double)ki, ii) ? 1 : 0;
+        }
+        if (r < a.k) {
+            const Real* q = a.raw + (cloud_row0 + ii) * D;
+            const double d0 = (double)q[0] - (double)mx, d1 = (double)q[1] - (double)my;
+            const double d2 = (D == 3) ? (double)q[D - 1] - (double)mz : 0.0;
+            const double dist = sqrt(exact_d2(d0, d1, d2));
+            const bool ok = dist < a.radius;         // exclusive bound, gicp.py:24
+            if (ok) {
+                ++n_valid;
+                // moments about the query point keep the scatter matrix accurate
+                mean[0] += d0; mean[1] += d1; mean[2] += d2;
+                S[0] += d0 * d0; S[1] += d0 * d1; S[2] += d0 * d2;
+                S[3] += d1 * d1; S[4] += d1 * d2; S[5] += d2 * d2;
+            }
+            if (out_idx) {
+                out_idx[r] = ok ? ii : -1;
+                if (out_d) out_d[r] = ok ? dist : INFINITY;
+            }
+        }
+    }
+    if (out_idx) {
+        for (int o = min(mcount, a.k); o < a.k; ++o) {
+            out_idx[o] = -1;
+            if (out_d) out_d[o] = INFINITY;
+        }
+    }
+    double C[NS];
+    const bool ident = n_valid <= 1;     // gicp.py:27,33-34
+    if (!ident) {
+        const double inv = 1.0 / n_valid;
+        const double m0 = mean[0] * inv, m1 = mean[1] * inv, m2 = mean[2] * inv;
+        const double f = 1.0 / (n_valid - 1);   // ddof = 1 (np.cov default, gicp.py:12)
+        S[0] = (S[0] - n_valid * m0 * m0) * f; S[1] = (S[1] - n_valid * m0 * m1) * f;
+        S[2] = (S[2] - n_valid * m0 * m2) * f; S[3] = (S[3] - n_valid * m1 * m1) * f;
+        S[4] = (S[4] - n_valid * m1 * m2) * f; S[5] = (S[5] - n_valid * m2 * m2) * f;
+    }
+    regularised_cov<D>(S, ident, a.lam_t, a.lam_n, C);
+    Real* out = a.cov_sorted + (size_t)s * NS;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) out[i] = (Real)C[i];
+}
+
 // ================================================================================================
 // fast path
 // ================================================================================================
@@ -245,83 +333,150 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Rea
     }
     if (!valid) return;
 
-    // ---- sweep 3: rank the list by counting; winners (rank < k) go to their sorted slot ----
-    const size_t cloud_row0 = (size_t)m.pt_begin;
-    auto exact_key = [&](int idx) {
-        const Real* q = a.raw + (cloud_row0 + idx) * D;
-        const double dz = (D == 3) ? (double)q[D - 1] - (double)mz : 0.0;
-        return exact_d2((double)q[0] - (double)mx, (double)q[1] - (double)my, dz);
-    };
-    int n_valid = 0;            // neighbours that pass the exact radius test
-    double mean[3] = {0.0, 0.0, 0.0};
-    double S[6] = {0, 0, 0, 0, 0, 0};
-    int* out_idx = a.knn_idx ? a.knn_idx + (cloud_row0 + my_idx) * (size_t)a.k : nullptr;
-    double* out_d = a.knn_dist ? a.knn_dist + (cloud_row0 + my_idx) * (size_t)a.k : nullptr;
-    for (int i = 0; i < mcount; ++i) {
-        const KeyT ki = lk[i * 32 + lane];
-        const int ii = li[i * 32 + lane];
-        int r = 0;
+    knn_rank_and_finish<D, Real>(a, m, base + lane, my_idx, mx, my, mz, lk, li, lane, mcount);
+}
+
+// ================================================================================================
+// fast path, per-lane variant: every lane walks the cells around its own query (ring by ring)
+// straight from L1/L2 - 32 lanes of a Morton-compact warp touch the same few cells - instead of
+// scanning the union of all 32 neighbourhoods.  Same three sweeps (histogram bound, list, rank).
+// ================================================================================================
+constexpr int KNN_LANE_WARP_SMEM = KNN_BINS * 32 + KNN_LIST_BYTES;
+
+template <int D, typename Real>
+__global__ void __launch_bounds__(KNN_THREADS) knn_lane_kernel(const KnnArgs<Real> a) {
+    using KeyT = Real;
+    constexpr int CAP = knn_list_cap<Real>();
+    constexpr int NS = Dim<D>::NS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* wbase = smem_raw + warp * KNN_LANE_WARP_SMEM;
+    unsigned char* hist = wbase;                                                   // [KNN_BINS][32] uint8
+    KeyT* lk = reinterpret_cast<KeyT*>(wbase + KNN_BINS * 32);                     // [CAP][32]
+    int* li = reinterpret_cast<int*>(wbase + KNN_BINS * 32 + CAP * 32 * sizeof(KeyT));
+
+    const int cloud = blockIdx.y;
+    const CloudMeta m = a.meta[cloud];
+    int begin = m.pt_begin, end = m.pt_end;
+    if (a.slice_begin >= 0) { begin = max(begin, a.slice_begin); end = min(end, a.slice_end); }
+    const int base = begin + (blockIdx.x * KNN_WARPS + warp) * 32;
+    if (base >= end) return;
+#pragma unroll
+    for (int b = 0; b < KNN_BINS; ++b) hist[b * 32 + lane] = 0;
+
+    const bool valid = base + lane < end;
+    const PRec<Real> me = a.spts[valid ? base + lane : end - 1];
+    const int my_idx = (int)me.idx;
+    const Real mx = me.x, my = me.y, mz = me.z;
+    const int cx = min(max(cell_coord((double)mx, m.origin[0], m.inv_h), 0), m.dims[0] - 1);
+    const int cy = min(max(cell_coord((double)my, m.origin[1], m.inv_h), 0), m.dims[1] - 1);
+    const int cz = (D == 3) ? min(max(cell_coord((double)mz, m.origin[2], m.inv_h), 0), m.dims[2] - 1) : 0;
+    const int* L = a.lut + m.lut_base;
+    const int* CS = a.cell_start + m.cell_base;
+
+    const double r2cap = a.radius * a.radius * (1.0 + 1e-12);
+    const float r2cap32 = __double2float_ru(r2cap * (1.0 + 1e-6));
+    const int ubase = (int)(__float_as_uint(r2cap32) >> 20) - (KNN_BINS - 1);
+    const float pad = cell_box_pad(m);
+    const int rho_max = max(1, (int)ceil(a.radius / (m.h * (1.0 - 1e-9))));
+
+    auto dist32 = [&](const PRec<Real>& c) {
         if (sizeof(Real) == 4) {
-            const float lo_k = (float)ki * 0.999999f, hi_k = (float)ki * 1.000001f;
-            int below = 0, upto = 0;
-            for (int j = 0; j < mcount; ++j) {
-                const float kj = (float)lk[j * 32 + lane];
-                below += (kj < lo_k) ? 1 : 0;
-                upto += (kj <= hi_k) ? 1 : 0;
-            }
-            r = below;
-            if (upto - below > 1) {   // another candidate inside the fp32 rounding band: exact keys decide
-                const double ei = exact_key(ii);
-                for (int j = 0; j < mcount; ++j) {
-                    const float kj = (float)lk[j * 32 + lane];
-                    if (j != i && kj >= lo_k && kj <= hi_k) {
-                        const int ij = li[j * 32 + lane];
-                        r += key_less(exact_key(ij), ij, ei, ii) ? 1 : 0;
-                    }
+            const float dx = (float)c.x - (float)mx, dy = (float)c.y - (float)my, dz = (float)c.z - (float)mz;
+            return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        } else {
+            return (float)exact_d2((double)c.x - (double)mx, (double)c.y - (double)my, (double)c.z - (double)mz);
+        }
+    };
+    auto hist_cell = [&](int x, int y, int z) {
+        const int* cs = CS + (__ldg(L + x) | __ldg(L + GICP_LUT_N + y) | __ldg(L + 2 * GICP_LUT_N + z));
+        const int j0 = __ldg(cs), j1 = __ldg(cs + 1);
+        for (int j = j0; j < j1; ++j) {
+            const float d2 = dist32(a.spts[j]);
+            const int g = min(max((int)(__float_as_uint(d2) >> 20) - ubase, 0), KNN_BINS - 1);
+            if (d2 <= r2cap32) hist[g * 32 + lane] += 1;
+        }
+    };
+
+    // ---- sweep 1: histogram the distances shell by shell ----
+    float bound32 = r2cap32;
+    int rho_fin = rho_max;
+    for (int rho = 0; rho <= rho_max; ++rho) {
+        const int z0 = (D == 3) ? max(cz - rho, 0) : 0, z1 = (D == 3) ? min(cz + rho, m.dims[2] - 1) : 0;
+        const int y0 = max(cy - rho, 0), y1 = min(cy + rho, m.dims[1] - 1);
+        const int x0 = max(cx - rho, 0), x1 = min(cx + rho, m.dims[0] - 1);
+        for (int z = z0; z <= z1; ++z)
+            for (int y = y0; y <= y1; ++y) {
+                const bool outer = (D == 3 && abs(z - cz) == rho) || abs(y - cy) == rho;
+                if (outer) {
+                    for (int x = x0; x <= x1; ++x) hist_cell(x, y, z);
+                } else {
+                    if (cx - rho >= 0) hist_cell(cx - rho, y, z);
+                    if (rho > 0 && cx + rho <= m.dims[0] - 1) hist_cell(cx + rho, y, z);
                 }
             }
-        } else {
-            for (int j = 0; j < mcount; ++j) r += key_less((double)lk[j * 32 + lane], li[j * 32 + lane], (double)ki, ii) ? 1 : 0;
+        // bin that holds the k-th candidate -> bound on the k-th neighbour distance
+        int cum = 0, kb = KNN_BINS;
+        for (int b = 0; b < KNN_BINS; ++b) {
+            cum += hist[b * 32 + lane];
+            if (cum >= a.k) { kb = b; break; }
         }
-        if (r < a.k) {
-            const Real* q = a.raw + (cloud_row0 + ii) * D;
-            const double d0 = (double)q[0] - (double)mx, d1 = (double)q[1] - (double)my;
-            const double d2 = (D == 3) ? (double)q[D - 1] - (double)mz : 0.0;
-            const double dist = sqrt(exact_d2(d0, d1, d2));
-            const bool ok = dist < a.radius;         // exclusive bound, gicp.py:24
-            if (ok) {
-                ++n_valid;
-                // moments about the query point keep the scatter matrix accurate
-                mean[0] += d0; mean[1] += d1; mean[2] += d2;
-                S[0] += d0 * d0; S[1] += d0 * d1; S[2] += d0 * d2;
-                S[3] += d1 * d1; S[4] += d1 * d2; S[5] += d2 * d2;
-            }
-            if (out_idx) {
-                out_idx[r] = ok ? ii : -1;
-                if (out_d) out_d[r] = ok ? dist : INFINITY;
-            }
-        }
-    }
-    if (out_idx) {
-        for (int o = min(mcount, a.k); o < a.k; ++o) {
-            out_idx[o] = -1;
-            if (out_d) out_d[o] = INFINITY;
-        }
-    }
-    double C[NS];
-    const bool ident = n_valid <= 1;     // gicp.py:27,33-34
-    if (!ident) {
-        const double inv = 1.0 / n_valid;
-        const double m0 = mean[0] * inv, m1 = mean[1] * inv, m2 = mean[2] * inv;
-        const double f = 1.0 / (n_valid - 1);   // ddof = 1 (np.cov default, gicp.py:12)
-        S[0] = (S[0] - n_valid * m0 * m0) * f; S[1] = (S[1] - n_valid * m0 * m1) * f;
-        S[2] = (S[2] - n_valid * m0 * m2) * f; S[3] = (S[3] - n_valid * m1 * m1) * f;
-        S[4] = (S[4] - n_valid * m1 * m2) * f; S[5] = (S[5] - n_valid * m2 * m2) * f;
-    }
-    regularised_cov<D>(S, ident, a.lam_t, a.lam_n, C);
-    Real* out = a.cov_sorted + (size_t)(base + lane) * NS;
+        const bool have = kb < KNN_BINS - 1;
+        const float edge2 = have ? __uint_as_float((unsigned)(ubase + kb + 1) << 20) : r2cap32;
+        // distance from the query to the nearest face of the searched box that has cells behind it
+        double cover = INFINITY;
+        {
+            const double q[3] = {(double)mx, (double)my, (double)mz};
+            const int c[3] = {cx, cy, cz};
 #pragma unroll
-    for (int i = 0; i < NS; ++i) out[i] = (Real)C[i];
+            for (int ax = 0; ax < D; ++ax) {
+                if (c[ax] - rho > 0) cover = fmin(cover, q[ax] - (m.origin[ax] + (c[ax] - rho) * m.h));
+                if (c[ax] + rho < m.dims[ax] - 1) cover = fmin(cover, m.origin[ax] + (c[ax] + rho + 1) * m.h - q[ax]);
+            }
+            cover *= (1.0 - 1e-9);
+        }
+        if ((have && (double)edge2 <= cover * cover) || cover >= a.radius) {
+            bound32 = fminf(edge2, r2cap32);
+            rho_fin = rho;
+            break;
+        }
+    }
+    // ---- sweep 2: keep the candidates under the bound (cells that reach into the ball only) ----
+    int cnt_l = 0;
+    {
+        const int z0 = (D == 3) ? max(cz - rho_fin, 0) : 0, z1 = (D == 3) ? min(cz + rho_fin, m.dims[2] - 1) : 0;
+        const int y0 = max(cy - rho_fin, 0), y1 = min(cy + rho_fin, m.dims[1] - 1);
+        const int x0 = max(cx - rho_fin, 0), x1 = min(cx + rho_fin, m.dims[0] - 1);
+        for (int z = z0; z <= z1; ++z)
+            for (int y = y0; y <= y1; ++y)
+                for (int x = x0; x <= x1; ++x) {
+                    if (cell_box_dist2(m, pad, (float)mx, (float)my, (float)mz, x, y, z, x, y, z) > bound32) continue;
+                    const int* cs = CS + (__ldg(L + x) | __ldg(L + GICP_LUT_N + y) | __ldg(L + 2 * GICP_LUT_N + z));
+                    const int j0 = __ldg(cs), j1 = __ldg(cs + 1);
+                    for (int j = j0; j < j1; ++j) {
+                        const PRec<Real> c = a.spts[j];
+                        KeyT key;
+                        if (sizeof(Real) == 4) key = (KeyT)dist32(c);
+                        else key = (KeyT)exact_d2((double)c.x - (double)mx, (double)c.y - (double)my,
+                                                  (double)c.z - (double)mz);
+                        if ((float)key <= bound32) {
+                            if (cnt_l < CAP) { lk[cnt_l * 32 + lane] = key; li[cnt_l * 32 + lane] = (int)c.idx; }
+                            ++cnt_l;
+                        }
+                    }
+                }
+    }
+    const int mcount = min(cnt_l, CAP);
+    // hand the whole warp to the general path if any lane's list overflowed
+    if (__any_sync(0xffffffffu, cnt_l > CAP)) {
+        if (lane == 0) {
+            const int slot = atomicAdd(a.overflow_count, 1);
+            if (slot < a.overflow_cap) a.overflow_list[slot] = make_int2(cloud, base);
+        }
+        return;
+    }
+    if (!valid) return;
+    knn_rank_and_finish<D, Real>(a, m, base + lane, my_idx, mx, my, mz, lk, li, lane, mcount);
 }
 
 // ================================================================================================

@@ -25,6 +25,7 @@ namespace gicp {
 constexpr int OBJ_THREADS = 128;
 constexpr int OBJ_STAGE_BYTES = 8192;  // per warp
 constexpr int OBJ_GROUP_REACH = 4;
+constexpr int OBJ_TRACK_MAX_CELLS = 8;
 
 template <typename Real> struct ObjArgs {
     const CloudMeta* src_meta;
@@ -49,6 +50,8 @@ template <typename Real> struct ObjArgs {
     double* out_W;
     int slice_begin, slice_end;
     int ignore_status;
+    int track_max_cells;      // per-lane walk only when the ball spans at most this many cells
+    int centre_first;
 };
 
 template <int D, typename Real>
@@ -163,13 +166,16 @@ __global__ void __launch_bounds__(OBJ_THREADS) objective_kernel(const ObjArgs<Re
             mylo[i] = (i < D) ? cell_coord(pp[i] - rad, mt.origin[i], mt.inv_h) : 0;
             myhi[i] = (i < D) ? cell_coord(pp[i] + rad, mt.origin[i], mt.inv_h) : 0;
         }
-        const bool tracked = bestpos >= 0;
+        // a lane walks its own cells only when they are few; wide balls (no previous match, or a
+        // match that moved far) are searched by the whole warp through the TMA stage
+        const int x0 = max(mylo[0], 0), x1 = min(myhi[0], mt.dims[0] - 1);
+        const int y0 = max(mylo[1], 0), y1 = min(myhi[1], mt.dims[1] - 1);
+        const int z0 = max(mylo[2], 0), z1 = min(myhi[2], mt.dims[2] - 1);
+        const int ncell = max(x1 - x0 + 1, 0) * max(y1 - y0 + 1, 0) * max(z1 - z0 + 1, 0);
+        const bool tracked = bestpos >= 0 && ncell <= a.track_max_cells;
         if (tracked) {
             // ---- phase A: per-lane walk over the (few) cells that intersect the ball ----
             const int* L = a.tgt_lut + mt.lut_base;
-            const int x0 = max(mylo[0], 0), x1 = min(myhi[0], mt.dims[0] - 1);
-            const int y0 = max(mylo[1], 0), y1 = min(myhi[1], mt.dims[1] - 1);
-            const int z0 = max(mylo[2], 0), z1 = min(myhi[2], mt.dims[2] - 1);
             for (int z = z0; z <= z1; ++z) {
                 const int lz = __ldg(L + 2 * GICP_LUT_N + z);
                 for (int y = y0; y <= y1; ++y) {
@@ -182,30 +188,41 @@ __global__ void __launch_bounds__(OBJ_THREADS) objective_kernel(const ObjArgs<Re
                 }
             }
         }
-        // ---- phase B: lanes without a usable previous match (first iteration, gated-out points):
-        //      warp-cooperative search of the whole d_max ball through the TMA stage ----
+        // ---- phase B: warp-cooperative search through the TMA stage.  First the cells the group's
+        //      points fall into (a near match shrinks every lane's ball at once), then the rest of
+        //      the union box, staging only the blocks that still reach into some lane's ball ----
         unsigned pending = __ballot_sync(0xffffffffu, !tracked);
         if (pending) {
             const int cx = cell_coord(pp[0], mt.origin[0], mt.inv_h);
             const int cy = cell_coord(pp[1], mt.origin[1], mt.inv_h);
             const int cz = (D == 3) ? cell_coord(pp[2], mt.origin[2], mt.inv_h) : 0;
+            const int mycell[3] = {cx, cy, cz};
             const int none[3] = {0, 0, 0};
             while (pending) {
                 const unsigned grp = next_group(pending, cx, cy, cz, OBJ_GROUP_REACH);
                 pending &= ~grp;
                 const bool mine = (grp >> lane) & 1u;
-                int lo[3], hi[3];
-                group_union(grp, lane, mylo, myhi, mt, lo, hi);
-                stream_cells<Real>(mt, a.tgt_cell_start, a.tgt_lut, a.tgt_spts, lo, hi, none, none, false, ws, lane,
-                                   [&](const PRec<Real>* w, int n) {
+                auto window = [&](const PRec<Real>* w, int n) {
                     for (int j = 0; j < n; ++j) {
                         const PRec<Real> c = w[j];
                         if (mine) test(c);
                     }
-                }, [&](int x0, int y0, int z0, int x1, int y1, int z1) {
+                };
+                auto need = [&](int bx0, int by0, int bz0, int bx1, int by1, int bz1) {
                     // only blocks that reach into some lane's current best-distance ball are staged
-                    return mine && cell_box_dist2(mt, pad, fx, fy, fz, x0, y0, z0, x1, y1, z1) <= thr32;
-                });
+                    return mine && cell_box_dist2(mt, pad, fx, fy, fz, bx0, by0, bz0, bx1, by1, bz1) <= thr32;
+                };
+                int clo[3], chi[3], lo[3], hi[3];
+                group_union(grp, lane, mycell, mycell, mt, clo, chi);
+                bool has_c = false;
+                if (a.centre_first) {
+                    stream_cells<Real>(mt, a.tgt_cell_start, a.tgt_lut, a.tgt_spts, clo, chi, none, none, false, ws,
+                                       lane, window, need);
+                    has_c = !(chi[0] < clo[0] || chi[1] < clo[1] || chi[2] < clo[2]);
+                }
+                group_union(grp, lane, mylo, myhi, mt, lo, hi);
+                stream_cells<Real>(mt, a.tgt_cell_start, a.tgt_lut, a.tgt_spts, lo, hi, clo, chi, has_c, ws, lane,
+                                   window, need);
             }
         }
         if (!valid) continue;
