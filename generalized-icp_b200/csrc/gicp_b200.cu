@@ -377,7 +377,7 @@ constexpr size_t OBJ_SMEM = 128 + (size_t)(OBJ_THREADS / 32) * OBJ_STAGE_BYTES;
 double auto_knn_cell(const gicpContext* h) {
     const double r = h->prm.max_distance_nearest_neighbors;
     if (h->prm.knn_cell > 0) return std::max(h->prm.knn_cell, r / 8.0);
-    return 0.25 * r;   // 2x2x2 cell blocks of r/2; measured optimum on the bench workload is r/5 .. r/4
+    return 0.4 * r;    // measured optimum of the per-lane fast path on the bench workload (r = 5 m -> 2 m cells)
 }
 double auto_nn_cell(const gicpContext* h) {
     const double r = h->prm.max_distance_correspondence;
@@ -468,7 +468,8 @@ int objective_args(gicpContext* h, ObjArgs<Real>& a, int& blocks_per_pair, bool 
     a.tgt_spts = T.nn.spts.as<PRec<Real>>();
     a.tgt_cov = T.cov_nn.as<Real>();
     a.tgt_perm = T.nn.perm.as<int>();
-    a.prev_match = nullptr;
+    a.match = nullptr;
+    a.use_prev = 0;
     CU(h->state.ensure((size_t)S.n_clouds * sizeof(PairState)));
     a.state = h->state.as<PairState>();
     a.T_override = nullptr;
@@ -496,6 +497,8 @@ int objective_args(gicpContext* h, ObjArgs<Real>& a, int& blocks_per_pair, bool 
     CU(h->partial.ensure((size_t)S.n_clouds * blocks_per_pair * Dim<D>::NRED * sizeof(double)));
     CU(h->red.ensure((size_t)S.n_clouds * Dim<D>::NRED * sizeof(double)));
     a.partial = h->partial.as<double>();
+    CU(h->prev_match.ensure((size_t)std::max<int64_t>(S.n_total, 1) * sizeof(int)));
+    a.match = h->prev_match.as<int>();
     return 0;
 }
 
@@ -531,9 +534,8 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
     CU(cudaMemcpyAsync(h->n_active.p, &np, sizeof(int), cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));
     // last iteration's match per source point (bounds the next search); -1 = none yet
-    CU(h->prev_match.ensure((size_t)std::max<int64_t>(h->src.n_total, 1) * sizeof(int)));
     CU(cudaMemsetAsync(h->prev_match.p, 0xFF, (size_t)std::max<int64_t>(h->src.n_total, 1) * sizeof(int), st));
-    oa.prev_match = h->prev_match.as<int>();
+    oa.use_prev = 1;
     SolveArgs sa;
     sa.partial = h->partial.as<double>();
     sa.blocks_per_pair = bpp;
@@ -558,7 +560,8 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
     for (int it = 0; it < h->prm.max_iterations; ++it) {
         {
             ProfScope prof(h, GICP_STAGE_OBJECTIVE, st);
-            objective_kernel<D, Real><<<ogrid, OBJ_THREADS, OBJ_SMEM, st>>>(oa);
+            correspond_kernel<D, Real><<<ogrid, OBJ_THREADS, OBJ_SMEM, st>>>(oa);
+            accumulate_kernel<D, Real><<<ogrid, OBJ_THREADS, 0, st>>>(oa);
         }
         ProfScope prof(h, GICP_STAGE_SOLVE, st);
         if (sharded) {
@@ -571,10 +574,10 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
             s2.partial = h->red.as<double>();
             s2.blocks_per_pair = 1;
             solve_kernel<D><<<sgrid, SOLVE_WARPS * 32, 0, st>>>(s2);
-            h->launches += 3;
+            h->launches += 4;
         } else {
             solve_kernel<D><<<sgrid, SOLVE_WARPS * 32, 0, st>>>(sa);
-            h->launches += 2;
+            h->launches += 3;
         }
         if ((it + 1) % poll_every == 0 || it + 1 == h->prm.max_iterations) {
             // progress poll: 4 bytes, the only host<->device traffic inside the loop
@@ -606,8 +609,9 @@ int do_stage(gicpContext* h, const double* h_T, int* d_idx, double* d_dist, doub
     oa.out_W = d_W;
     oa.ignore_status = 1;
     // stage entry points always cover the whole source (no slicing), so their outputs are complete
-    objective_kernel<D, Real><<<dim3(bpp, np), OBJ_THREADS, OBJ_SMEM, st>>>(oa);
-    h->launches += 1;
+    correspond_kernel<D, Real><<<dim3(bpp, np), OBJ_THREADS, OBJ_SMEM, st>>>(oa);
+    if (d_W || h_out) accumulate_kernel<D, Real><<<dim3(bpp, np), OBJ_THREADS, 0, st>>>(oa);
+    h->launches += 2;
     if (h_out) {
         SolveArgs sa;
         memset(&sa, 0, sizeof sa);

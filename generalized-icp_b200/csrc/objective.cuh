@@ -38,7 +38,10 @@ template <typename Real> struct ObjArgs {
     const Real* tgt_cov;
     const int* src_perm;          // sorted position -> cloud-local input index
     const int* tgt_perm;
-    int* prev_match;              // optional [n_src_total], source nn order: last iteration's match (position) or -1
+    int* match;                   // [n_src_total], source nn order: matched target position or -1.  Written by
+                                  // correspond_kernel, read by accumulate_kernel; with use_prev the previous
+                                  // iteration's match bounds the next search
+    int use_prev;
     const PairState* state;
     const double* T_override;  // optional [n_pairs][(D+1)^2], device
     double* partial;           // [n_pairs][blocks_per_pair][NRED]
@@ -55,10 +58,7 @@ template <typename Real> struct ObjArgs {
 };
 
 template <int D, typename Real>
-__global__ void __launch_bounds__(OBJ_THREADS) objective_kernel(const ObjArgs<Real> a) {
-    using DD = Dim<D>;
-    using AccT = Real;
-    constexpr int NP = DD::NP, NS = DD::NS, NH = DD::NH, NQ = DD::NQ, NRED = DD::NRED;
+__global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<Real> a) {
     const int pair = blockIdx.y;
     const PairState st = a.state[pair];
     if (!a.ignore_status && st.status != PAIR_ACTIVE) return;
@@ -97,12 +97,6 @@ __global__ void __launch_bounds__(OBJ_THREADS) objective_kernel(const ObjArgs<Re
     if (lane == 0) { mbar_init(ws.bar, 1); mbar_fence_init(); }
     __syncwarp();
 
-    AccT acc[NQ];
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) acc[i] = AccT(0);
-    double loss_acc = 0.0;
-    int cnt = 0;
-
     for (int it = 0; it < a.ppt; ++it) {
         const int wbase = begin + (blockIdx.x * a.ppt + it) * OBJ_THREADS + warp * 32;
         if (wbase >= end) break;  // warp-uniform
@@ -125,8 +119,8 @@ __global__ void __launch_bounds__(OBJ_THREADS) objective_kernel(const ObjArgs<Re
         //      that intersect the ball of that radius around p' are searched (still exact). ----
         double bestd = d2cap;
         int bestpos = -1;
-        if (a.prev_match) {
-            const int pm = a.prev_match[valid ? s : end - 1];
+        if (a.use_prev) {
+            const int pm = a.match[valid ? s : end - 1];
             if (pm >= 0) {
                 const PRec<Real> qo = a.tgt_spts[pm];
                 const double e2 = exact_d2((double)qo.x - pp[0], (double)qo.y - pp[1], (double)qo.z - pp[2]);
@@ -228,15 +222,74 @@ __global__ void __launch_bounds__(OBJ_THREADS) objective_kernel(const ObjArgs<Re
         if (!valid) continue;
         const double dist = (bestpos >= 0) ? sqrt(bestd) : INFINITY;
         const bool matched = (bestpos >= 0) && !(dist > a.d_max);  // gicp.py:136 rejects d > d_max
-        if (a.prev_match) a.prev_match[s] = matched ? bestpos : -1;
-        const size_t out_row = (size_t)ms.pt_begin + (size_t)a.src_perm[s];
-        if (a.out_idx) a.out_idx[out_row] = matched ? a.tgt_perm[bestpos] : -1;
-        if (a.out_dist) a.out_dist[out_row] = dist;
-        if (!matched) {
+        a.match[s] = matched ? bestpos : -1;
+        if (a.out_idx || a.out_dist) {
+            const size_t out_row = (size_t)ms.pt_begin + (size_t)a.src_perm[s];
+            if (a.out_idx) a.out_idx[out_row] = matched ? a.tgt_perm[bestpos] : -1;
+            if (a.out_dist) a.out_dist[out_row] = dist;
+        }
+    }
+}
+
+template <int D, typename Real>
+__global__ void __launch_bounds__(OBJ_THREADS) accumulate_kernel(const ObjArgs<Real> a) {
+    using DD = Dim<D>;
+    using AccT = Real;
+    constexpr int NP = DD::NP, NS = DD::NS, NH = DD::NH, NQ = DD::NQ, NRED = DD::NRED;
+    const int pair = blockIdx.y;
+    const PairState st = a.state[pair];
+    if (!a.ignore_status && st.status != PAIR_ACTIVE) return;
+
+    double R[D][D], t[D];
+    if (a.T_override) {
+        const double* T = a.T_override + (size_t)pair * (D + 1) * (D + 1);
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) R[i][j] = T[i * (D + 1) + j];
+            t[i] = T[i * (D + 1) + D];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) R[i][j] = st.R[i * 3 + j];
+            t[i] = st.t[i];
+        }
+    }
+    const CloudMeta ms = a.src_meta[pair];
+    const CloudMeta mt = a.tgt_meta[pair];
+    int begin = ms.pt_begin, end = ms.pt_end;
+    if (a.slice_begin >= 0) { begin = max(begin, a.slice_begin); end = min(end, a.slice_end); }
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    AccT acc[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) acc[i] = AccT(0);
+    double loss_acc = 0.0;
+    int cnt = 0;
+
+    for (int it = 0; it < a.ppt; ++it) {
+        const int s = begin + (blockIdx.x * a.ppt + it) * OBJ_THREADS + threadIdx.x;
+        if (s >= end) break;
+        const int bestpos = a.match[s];
+        const size_t out_row = (size_t)ms.pt_begin + (size_t)(a.out_W ? a.src_perm[s] : 0);
+        if (bestpos < 0) {
             if (a.out_W) {
                 for (int i = 0; i < D * D; ++i) a.out_W[out_row * D * D + i] = 0.0;
             }
             continue;
+        }
+        const PRec<Real> p = a.src_spts[s];
+        double pp[3] = {0.0, 0.0, 0.0};  // p' = R p + t (gicp.py:119)
+        {
+            const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                double v = R[i][0] * px + R[i][1] * py + t[i];
+                if constexpr (D == 3) v += R[i][2] * pz;
+                pp[i] = v;
+            }
         }
         // ---- W = inv(C_tgt[j] + R C_src[i] R^T), e = q - p' ----
         const PRec<Real> q = a.tgt_spts[bestpos];
