@@ -415,23 +415,21 @@ int set_cloud(gicpContext* h, int which, const void* d_points, const int64_t* h_
     if (build_grid<D, Real>(h, cs, cs.knn, h_knn, true, false, st)) return 1;
     CU(cs.cov_knn.ensure((size_t)std::max<int64_t>(cs.n_total, 1) * ns_of(D) * sizeof(Real)));
 
-    // covariances; in sharded mode the target slice is computed locally and all-gathered
+    // covariances; in sharded mode every rank computes an equal slice (k-NN grid order) of BOTH clouds
+    // and the slices are all-gathered: the correspondence stage walks the clouds in a different
+    // (1-NN grid) order, so every rank needs every covariance
     int slice_b = -1, slice_e = -1;
-    if (h->comm && n_clouds == 1) {
+    const bool sharded = h->comm && n_clouds == 1;
+    int64_t per = 0;
+    if (sharded) {
         const int64_t n = cs.n_total;
-        slice_b = (int)(n * h->rank / h->n_ranks);
-        slice_e = (int)(n * (h->rank + 1) / h->n_ranks);
-        if (which == GICP_TARGET) {
-            // equal-sized slices are required by ncclAllGather: round the slice length up
-            const int64_t per = (n + h->n_ranks - 1) / h->n_ranks;
-            slice_b = (int)std::min<int64_t>(n, per * h->rank);
-            slice_e = (int)std::min<int64_t>(n, per * (h->rank + 1));
-            CU(cs.cov_knn.ensure((size_t)per * h->n_ranks * ns_of(D) * sizeof(Real)));
-        }
+        per = (n + h->n_ranks - 1) / h->n_ranks;   // equal-sized slices are required by ncclAllGather
+        slice_b = (int)std::min<int64_t>(n, per * h->rank);
+        slice_e = (int)std::min<int64_t>(n, per * (h->rank + 1));
+        CU(cs.cov_knn.ensure((size_t)per * h->n_ranks * ns_of(D) * sizeof(Real)));
     }
     if (launch_knn<D, Real>(h, cs, nullptr, nullptr, st, slice_b, slice_e)) return 1;
-    if (h->comm && n_clouds == 1 && which == GICP_TARGET) {
-        const int64_t per = (cs.n_total + h->n_ranks - 1) / h->n_ranks;
+    if (sharded) {
         const size_t bytes = (size_t)per * ns_of(D) * sizeof(Real);
         char* basep = cs.cov_knn.as<char>();
         int rc = g_nccl.AllGather(basep + bytes * h->rank, basep, bytes, NCCL_INT8, h->comm, st);
