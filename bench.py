@@ -243,10 +243,11 @@ def run_b200(args):
     pts_rank = 2 * my_pairs * args.points
     iters_sum = int(n_outer.sum())
     stage_bytes = {   # ALGORITHMIC bytes per step on this rank (SURVEY 8d / DESIGN.md)
-        "grid_build": 36.0 * pts_rank,
+        "grid_build": 36.0 * 2 * pts_rank,                 # two grids per cloud (k-NN order, 1-NN order)
         "knn_cov": 40.0 * pts_rank,
-        "objective": 80.0 * iters_sum * args.points,
-        "solve": 0.0,
+        "correspond": 36.0 * iters_sum * args.points,      # source point + match index + matched target point
+        "accumulate": 80.0 * iters_sum * args.points,      # both points + both covariances
+        "solve": 640.0 * iters_sum,
     }
     peaks = {}
     try:
@@ -260,15 +261,23 @@ def run_b200(args):
         gbs = stage_bytes[st] / (ms_st * 1e-3) / 1e9 if ms_st > 0 else 0.0
         kernels[st] = {"ms_per_step": ms_st, "launches": cnt, "algorithmic_gb": stage_bytes[st] / 1e9,
                        "achieved_gbs": gbs, "frac": gbs / peak}
-    dom = max(("knn_cov", "objective", "grid_build"), key=lambda s: kernels[s]["ms_per_step"])
-    traffic = None
+    dom = max(("knn_cov", "correspond", "accumulate", "grid_build"), key=lambda s: kernels[s]["ms_per_step"])
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (a smaller batch of the
+    # same workload), scaled per point to this launch
+    traffic, traffic_note = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj.get(dom, {}).get("dram_bytes_per_launch")
+        cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.startswith("traffic_"))
+        tj = json.load(open(os.path.join(ROOT, "profiles", cands[-1])))
+        kname = {"knn_cov": "knn_lane_kernel", "correspond": "correspond_kernel", "accumulate": "accumulate_kernel"}[dom]
+        per_pt = sum(tj["launches"][kname]) / len(tj["launches"][kname]) / tj["points_per_launch"]
+        units = kernels[dom]["launches"]
+        pts_per_launch = (pts_rank / 2) if dom == "knn_cov" else iters_sum * args.points / max(1, units)
+        traffic = per_pt * pts_per_launch
+        traffic_note = f"{cands[-1]}: {per_pt:.1f} B/point measured on a 64-pair batch, scaled to this launch"
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                 "avg_launch_ms": kernels[dom]["ms_per_step"] / max(1, kernels[dom]["launches"]),
                 "kernels": kernels}
 

@@ -557,8 +557,11 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
     const int poll_every = 2;
     for (int it = 0; it < h->prm.max_iterations; ++it) {
         {
-            ProfScope prof(h, GICP_STAGE_OBJECTIVE, st);
+            ProfScope prof(h, GICP_STAGE_CORRESPOND, st);
             correspond_kernel<D, Real><<<ogrid, OBJ_THREADS, OBJ_SMEM, st>>>(oa);
+        }
+        {
+            ProfScope prof(h, GICP_STAGE_ACCUMULATE, st);
             accumulate_kernel<D, Real><<<ogrid, OBJ_THREADS, 0, st>>>(oa);
         }
         ProfScope prof(h, GICP_STAGE_SOLVE, st);

@@ -182,15 +182,15 @@ class GicpEngine:
     def comm_destroy(self):
         _lib.check(self.lib.gicpCommDestroy(self._h))
 
-    STAGES = ("grid_build", "knn_cov", "objective", "solve")
+    STAGES = ("grid_build", "knn_cov", "correspond", "accumulate", "solve")
 
     def profile(self, enable=True):
         _lib.check(self.lib.gicpProfile(self._h, int(bool(enable))))
 
     def profile_read(self):
         """{stage: (milliseconds, timed sections)} since the last read (device-synchronising)."""
-        ms = (C.c_double * 4)()
-        cnt = (C.c_int64 * 4)()
+        ms = (C.c_double * 5)()
+        cnt = (C.c_int64 * 5)()
         _lib.check(self.lib.gicpProfileRead(self._h, ms, cnt))
         return {s: (float(ms[i]), int(cnt[i])) for i, s in enumerate(self.STAGES)}
 

@@ -130,7 +130,8 @@ int64_t gicpLaunchCount(gicpHandle h);
 /* per-stage device timing with CUDA events on the launching stream (bench.py's roofline leg).
  * gicpProfile(h, 1) starts recording; gicpProfileRead synchronises the device, returns the summed
  * milliseconds and the number of timed launches/sections per stage, and clears the records.   */
-enum { GICP_STAGE_GRID = 0, GICP_STAGE_KNN_COV = 1, GICP_STAGE_OBJECTIVE = 2, GICP_STAGE_SOLVE = 3, GICP_N_STAGES = 4 };
+enum { GICP_STAGE_GRID = 0, GICP_STAGE_KNN_COV = 1, GICP_STAGE_CORRESPOND = 2, GICP_STAGE_ACCUMULATE = 3,
+       GICP_STAGE_SOLVE = 4, GICP_N_STAGES = 5 };
 int gicpProfile(gicpHandle h, int enable);
 int gicpProfileRead(gicpHandle h, double ms_out[GICP_N_STAGES], int64_t count_out[GICP_N_STAGES]);
 
