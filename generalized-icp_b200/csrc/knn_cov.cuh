@@ -102,7 +102,7 @@ __device__ __forceinline__ void regularised_cov(const double S[6], bool ident, d
 template <int D, typename Real>
 __device__ __forceinline__ void knn_rank_and_finish(const KnnArgs<Real>& a, const CloudMeta& m, int s, int my_idx,
                                                     Real mx, Real my, Real mz, const Real* lk, const int* li,
-                                                    int lane, int mcount) {
+                                                    int lane, int mcount, float edge_lo) {
     using KeyT = Real;
     constexpr int NS = Dim<D>::NS;
     // ---- sweep 3: rank the list by counting; winners (rank < k) go to their sorted slot ----
@@ -117,11 +117,23 @@ __device__ __forceinline__ void knn_rank_and_finish(const KnnArgs<Real>& a, cons
     double S[6] = {0, 0, 0, 0, 0, 0};
     int* out_idx = a.knn_idx ? a.knn_idx + (cloud_row0 + my_idx) * (size_t)a.k : nullptr;
     double* out_d = a.knn_dist ? a.knn_dist + (cloud_row0 + my_idx) * (size_t)a.k : nullptr;
+    // Only the SET of the k nearest matters for the covariance.  Every candidate below the k-th
+    // histogram bin is in it for sure (fewer than k candidates lie below that bin); only the candidates
+    // of the k-th bin compete for the remaining k - n_sure places and need ranking.  The 4e-6 margin
+    // keeps "sure" exact under fp32 rounding: an excluded candidate is farther than some candidate of
+    // the k-th bin, hence farther than every sure one.  With index output the whole list is ranked.
+    const bool need_order = a.knn_idx != nullptr;
+    float sure_thr = need_order ? -1.0f : ((sizeof(Real) == 4) ? edge_lo * (1.0f - 4e-6f) : edge_lo);
+    int n_sure = 0;
+    for (int j = 0; j < mcount; ++j) n_sure += ((float)lk[j * 32 + lane] < sure_thr) ? 1 : 0;
+    if (n_sure >= a.k) sure_thr = -1.0f;   // only possible if an 8-bit histogram counter wrapped: rank everything
     for (int i = 0; i < mcount; ++i) {
         const KeyT ki = lk[i * 32 + lane];
         const int ii = li[i * 32 + lane];
         int r = 0;
-        if (sizeof(Real) == 4) {
+        if ((float)ki < sure_thr) {
+            r = 0;                       // included; its rank is not needed
+        } else if (sizeof(Real) == 4) {
             const float lo_k = (float)ki * 0.999999f, hi_k = (float)ki * 1.000001f;
             int below = 0, upto = 0;
             for (int j = 0; j < mcount; ++j) {
@@ -333,7 +345,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Rea
     }
     if (!valid) return;
 
-    knn_rank_and_finish<D, Real>(a, m, base + lane, my_idx, mx, my, mz, lk, li, lane, mcount);
+    knn_rank_and_finish<D, Real>(a, m, base + lane, my_idx, mx, my, mz, lk, li, lane, mcount, 0.0f);
 }
 
 // ================================================================================================
@@ -388,55 +400,81 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_lane_kernel(const KnnArgs<Rea
             return (float)exact_d2((double)c.x - (double)mx, (double)c.y - (double)my, (double)c.z - (double)mz);
         }
     };
-    auto hist_cell = [&](int x, int y, int z) {
+    // ---- sweep 1: histogram the distances, nearest cells first ----
+    // Shell 1 is walked as faces, then edges, then corners; between the classes the histogram is
+    // consulted, and a cell whose box lies beyond the current bound on the k-th distance is skipped
+    // (none of its points can be among the k nearest).
+    float bound32 = r2cap32;
+    float edge_lo = 0.0f;
+    int rho_fin = rho_max;
+    int seen = 0;
+    const float qx = (float)mx, qy = (float)my, qz = (float)mz;
+    auto visit = [&](int x, int y, int z) {
+        if (x < 0 || y < 0 || z < 0 || x >= m.dims[0] || y >= m.dims[1] || z >= m.dims[2]) return;
+        if (cell_box_dist2(m, pad, qx, qy, qz, x, y, z, x, y, z) > bound32) return;
         const int* cs = CS + (__ldg(L + x) | __ldg(L + GICP_LUT_N + y) | __ldg(L + 2 * GICP_LUT_N + z));
         const int j0 = __ldg(cs), j1 = __ldg(cs + 1);
         for (int j = j0; j < j1; ++j) {
             const float d2 = dist32(a.spts[j]);
             const int g = min(max((int)(__float_as_uint(d2) >> 20) - ubase, 0), KNN_BINS - 1);
-            if (d2 <= r2cap32) hist[g * 32 + lane] += 1;
+            if (d2 <= r2cap32) { hist[g * 32 + lane] += 1; ++seen; }
         }
     };
-
-    // ---- sweep 1: histogram the distances shell by shell ----
-    float bound32 = r2cap32;
-    int rho_fin = rho_max;
-    for (int rho = 0; rho <= rho_max; ++rho) {
-        const int z0 = (D == 3) ? max(cz - rho, 0) : 0, z1 = (D == 3) ? min(cz + rho, m.dims[2] - 1) : 0;
-        const int y0 = max(cy - rho, 0), y1 = min(cy + rho, m.dims[1] - 1);
-        const int x0 = max(cx - rho, 0), x1 = min(cx + rho, m.dims[0] - 1);
-        for (int z = z0; z <= z1; ++z)
-            for (int y = y0; y <= y1; ++y) {
-                const bool outer = (D == 3 && abs(z - cz) == rho) || abs(y - cy) == rho;
-                if (outer) {
-                    for (int x = x0; x <= x1; ++x) hist_cell(x, y, z);
-                } else {
-                    if (cx - rho >= 0) hist_cell(cx - rho, y, z);
-                    if (rho > 0 && cx + rho <= m.dims[0] - 1) hist_cell(cx + rho, y, z);
-                }
-            }
-        // bin that holds the k-th candidate -> bound on the k-th neighbour distance
-        int cum = 0, kb = KNN_BINS;
+    // bin of the k-th candidate so far -> (lower edge, upper edge) of that bin; false if fewer than k
+    auto kth_bin = [&](float& lo_e, float& hi_e) {
+        if (seen < a.k) return false;
+        int cum = 0, kb = KNN_BINS - 1;
         for (int b = 0; b < KNN_BINS; ++b) {
             cum += hist[b * 32 + lane];
             if (cum >= a.k) { kb = b; break; }
         }
-        const bool have = kb < KNN_BINS - 1;
-        const float edge2 = have ? __uint_as_float((unsigned)(ubase + kb + 1) << 20) : r2cap32;
+        // every candidate of bins <= kb has d2 < hi_e (exact: bin edges are float bit patterns)
+        lo_e = (kb > 0) ? __uint_as_float((unsigned)(ubase + kb) << 20) : 0.0f;
+        hi_e = (kb < KNN_BINS - 1) ? __uint_as_float((unsigned)(ubase + kb + 1) << 20) : r2cap32;
+        return true;
+    };
+    auto cover_of = [&](int rho) {
         // distance from the query to the nearest face of the searched box that has cells behind it
         double cover = INFINITY;
-        {
-            const double q[3] = {(double)mx, (double)my, (double)mz};
-            const int c[3] = {cx, cy, cz};
+        const double q[3] = {(double)mx, (double)my, (double)mz};
+        const int c[3] = {cx, cy, cz};
 #pragma unroll
-            for (int ax = 0; ax < D; ++ax) {
-                if (c[ax] - rho > 0) cover = fmin(cover, q[ax] - (m.origin[ax] + (c[ax] - rho) * m.h));
-                if (c[ax] + rho < m.dims[ax] - 1) cover = fmin(cover, m.origin[ax] + (c[ax] + rho + 1) * m.h - q[ax]);
-            }
-            cover *= (1.0 - 1e-9);
+        for (int ax = 0; ax < D; ++ax) {
+            if (c[ax] - rho > 0) cover = fmin(cover, q[ax] - (m.origin[ax] + (c[ax] - rho) * m.h));
+            if (c[ax] + rho < m.dims[ax] - 1) cover = fmin(cover, m.origin[ax] + (c[ax] + rho + 1) * m.h - q[ax]);
         }
-        if ((have && (double)edge2 <= cover * cover) || cover >= a.radius) {
-            bound32 = fminf(edge2, r2cap32);
+        return cover * (1.0 - 1e-9);
+    };
+    for (int rho = 0; rho <= rho_max; ++rho) {
+        if (rho == 0) {
+            visit(cx, cy, cz);
+        } else if (rho == 1) {
+            for (int cls = 1; cls <= D; ++cls) {
+                for (int dz = (D == 3) ? -1 : 0; dz <= ((D == 3) ? 1 : 0); ++dz)
+                    for (int dy = -1; dy <= 1; ++dy)
+                        for (int dx = -1; dx <= 1; ++dx)
+                            if (abs(dx) + abs(dy) + abs(dz) == cls) visit(cx + dx, cy + dy, cz + dz);
+                float lo_e, hi_e;
+                if (kth_bin(lo_e, hi_e)) bound32 = fminf(bound32, hi_e);
+            }
+        } else {
+            for (int dz = (D == 3) ? -rho : 0; dz <= ((D == 3) ? rho : 0); ++dz)
+                for (int dy = -rho; dy <= rho; ++dy) {
+                    const bool outer = abs(dz) == rho || abs(dy) == rho;
+                    if (outer) {
+                        for (int dx = -rho; dx <= rho; ++dx) visit(cx + dx, cy + dy, cz + dz);
+                    } else {
+                        visit(cx - rho, cy + dy, cz + dz);
+                        visit(cx + rho, cy + dy, cz + dz);
+                    }
+                }
+        }
+        float lo_e = 0.0f, hi_e = r2cap32;
+        const bool have = kth_bin(lo_e, hi_e);
+        if (have) bound32 = fminf(bound32, hi_e);
+        const double cover = cover_of(rho);
+        if ((have && (double)bound32 <= cover * cover) || cover >= a.radius) {
+            edge_lo = have ? lo_e : 0.0f;
             rho_fin = rho;
             break;
         }
@@ -476,7 +514,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_lane_kernel(const KnnArgs<Rea
         return;
     }
     if (!valid) return;
-    knn_rank_and_finish<D, Real>(a, m, base + lane, my_idx, mx, my, mz, lk, li, lane, mcount);
+    knn_rank_and_finish<D, Real>(a, m, base + lane, my_idx, mx, my, mz, lk, li, lane, mcount, edge_lo);
 }
 
 // ================================================================================================
