@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Rea
     const float pad = cell_box_pad(m);
     const int rho_max = max(1, (int)ceil(a.radius / (m.h * (1.0 - 1e-9))));
     float bound32 = r2cap32;   // squared-distance bound under which at least k candidates lie
+    float edge_lo = 0.0f;      // lower edge of the histogram bin that holds the k-th candidate
     bool overflow = false;
     int mcount = 0;
 
@@ -267,7 +268,10 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Rea
         group_union(grp, lane, mycell, mycell, m, qlo, qhi);
         int plo[3] = {0, 0, 0}, phi[3] = {-1, -1, -1};
         int lo[3] = {0, 0, 0}, hi[3] = {-1, -1, -1};
-        // ---- sweep 1: histogram the distances ring by ring ----
+        // ---- sweep 1: histogram the distances ring by ring.  After every ring the histogram bounds
+        //      the lane's k-th distance; blocks beyond every lane's bound are not staged ----
+        float prov32 = r2cap32;
+        int seen = 0;
         for (int rho = 0; rho <= rho_max; ++rho) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) { lo[c] = max(qlo[c] - rho, 0); hi[c] = min(qhi[c] + rho, m.dims[c] - 1); }
@@ -281,34 +285,44 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Rea
                     const int g1 = min(max((int)(__float_as_uint(e1) >> 20) - ubase, 0), KNN_BINS - 1);
                     const int g2 = min(max((int)(__float_as_uint(e2) >> 20) - ubase, 0), KNN_BINS - 1);
                     const int g3 = min(max((int)(__float_as_uint(e3) >> 20) - ubase, 0), KNN_BINS - 1);
-                    if (mine && e0 <= r2cap32) hist[g0 * 32 + lane] += 1;
-                    if (mine && e1 <= r2cap32) hist[g1 * 32 + lane] += 1;
-                    if (mine && e2 <= r2cap32) hist[g2 * 32 + lane] += 1;
-                    if (mine && e3 <= r2cap32) hist[g3 * 32 + lane] += 1;
+                    if (mine && e0 <= r2cap32) { hist[g0 * 32 + lane] += 1; ++seen; }
+                    if (mine && e1 <= r2cap32) { hist[g1 * 32 + lane] += 1; ++seen; }
+                    if (mine && e2 <= r2cap32) { hist[g2 * 32 + lane] += 1; ++seen; }
+                    if (mine && e3 <= r2cap32) { hist[g3 * 32 + lane] += 1; ++seen; }
                 }
                 for (; j < n; ++j) {
                     const float e0 = dist32(w[j]);
                     const int g0 = min(max((int)(__float_as_uint(e0) >> 20) - ubase, 0), KNN_BINS - 1);
-                    if (mine && e0 <= r2cap32) hist[g0 * 32 + lane] += 1;
+                    if (mine && e0 <= r2cap32) { hist[g0 * 32 + lane] += 1; ++seen; }
                 }
+            }, [&](int x0, int y0, int z0, int x1, int y1, int z1) {
+                return mine && cell_box_dist2(m, pad, (float)mx, (float)my, (float)mz, x0, y0, z0, x1, y1, z1) <= prov32;
             });
 #pragma unroll
             for (int c = 0; c < 3; ++c) { plo[c] = lo[c]; phi[c] = hi[c]; }
-            if (rho == 0) continue;
             // bin that holds the k-th candidate -> bound on the k-th neighbour distance.  (A counter
             // that wrapped at 256 only makes the bound larger, never wrong.)
-            int cum = 0, kb = KNN_BINS;
-            for (int b = 0; b < KNN_BINS; ++b) {
-                cum += hist[b * 32 + lane];
-                if (cum >= a.k) { kb = b; break; }
+            int kb = KNN_BINS - 1;
+            bool have = false;
+            if (seen >= a.k) {
+                int cum = 0;
+                for (int b = 0; b < KNN_BINS; ++b) {
+                    cum += hist[b * 32 + lane];
+                    if (cum >= a.k) { kb = b; break; }
+                }
+                have = kb < KNN_BINS - 1;
             }
             // every candidate of bins <= kb has d2 < edge2 (exact: bin edges are float bit patterns)
-            const bool have = kb < KNN_BINS - 1;
             const float edge2 = have ? __uint_as_float((unsigned)(ubase + kb + 1) << 20) : r2cap32;
+            prov32 = fminf(prov32, edge2);
+            if (rho == 0) continue;
             const double cover = rho * m.h * (1.0 - 1e-9);
-            const bool mine_done = !mine || (have && (double)edge2 <= cover * cover);
+            const bool mine_done = !mine || (have && (double)prov32 <= cover * cover);
             if (__all_sync(0xffffffffu, mine_done) || cover >= a.radius) {
-                if (mine) bound32 = fminf(edge2, r2cap32);
+                if (mine) {
+                    bound32 = prov32;
+                    edge_lo = (have && kb > 0) ? __uint_as_float((unsigned)(ubase + kb) << 20) : 0.0f;
+                }
                 break;
             }
         }
@@ -345,7 +359,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Rea
     }
     if (!valid) return;
 
-    knn_rank_and_finish<D, Real>(a, m, base + lane, my_idx, mx, my, mz, lk, li, lane, mcount, 0.0f);
+    knn_rank_and_finish<D, Real>(a, m, base + lane, my_idx, mx, my, mz, lk, li, lane, mcount, edge_lo);
 }
 
 // ================================================================================================
@@ -353,7 +367,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Rea
 // straight from L1/L2 - 32 lanes of a Morton-compact warp touch the same few cells - instead of
 // scanning the union of all 32 neighbourhoods.  Same three sweeps (histogram bound, list, rank).
 // ================================================================================================
-constexpr int KNN_LANE_WARP_SMEM = KNN_BINS * 32 + KNN_LIST_BYTES;
+constexpr int KNN_LANE_WARP_SMEM = KNN_LIST_BYTES;   // the histogram (sweep 1) and the list (sweeps 2-3) share it
 
 template <int D, typename Real>
 __global__ void __launch_bounds__(KNN_THREADS) knn_lane_kernel(const KnnArgs<Real> a) {
@@ -363,9 +377,9 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_lane_kernel(const KnnArgs<Rea
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* wbase = smem_raw + warp * KNN_LANE_WARP_SMEM;
-    unsigned char* hist = wbase;                                                   // [KNN_BINS][32] uint8
-    KeyT* lk = reinterpret_cast<KeyT*>(wbase + KNN_BINS * 32);                     // [CAP][32]
-    int* li = reinterpret_cast<int*>(wbase + KNN_BINS * 32 + CAP * 32 * sizeof(KeyT));
+    unsigned char* hist = wbase;                                                   // [KNN_BINS][32] uint8, sweep 1
+    KeyT* lk = reinterpret_cast<KeyT*>(wbase);                                     // [CAP][32], sweeps 2-3 (aliases hist)
+    int* li = reinterpret_cast<int*>(wbase + CAP * 32 * sizeof(KeyT));
 
     const int cloud = blockIdx.y;
     const CloudMeta m = a.meta[cloud];
@@ -480,6 +494,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_lane_kernel(const KnnArgs<Rea
         }
     }
     // ---- sweep 2: keep the candidates under the bound (cells that reach into the ball only) ----
+    __syncwarp();   // every lane is done with its histogram column before the list overwrites the memory
     int cnt_l = 0;
     {
         const int z0 = (D == 3) ? max(cz - rho_fin, 0) : 0, z1 = (D == 3) ? min(cz + rho_fin, m.dims[2] - 1) : 0;
