@@ -52,6 +52,8 @@ struct PairState {
     double theta;       // dim 2: accumulated angle (the reference rebuilds T from it, gicp.py:166)
     double last_loss;   // gicp.py:110,165
     double mu[3];       // centring point of the reduced form (target bbox centre)
+    double Rp[9];       // transform of the previous outer iteration (how far each point moved since)
+    double tp[3];
     int iter;           // outer iterations completed
     int status;
     int converged_at;   // gicp.py:161 or -1

@@ -127,7 +127,7 @@ struct gicpContext {
     gicpParams prm;
     CloudSet src, tgt;
     DevBuf keys, keys_alt, vals, vals_alt, cub_tmp, cell_count, bbox_part, knn_idx_tmp;
-    DevBuf state, partial, red, T_dev, n_active, prev_match, ovf_count, ovf_list;
+    DevBuf state, partial, red, T_dev, n_active, prev_match, slack, ovf_count, ovf_list;
     int* h_poll = nullptr;  // pinned
     cudaEvent_t poll_event = nullptr;
     int64_t launches = 0;
@@ -497,6 +497,8 @@ int objective_args(gicpContext* h, ObjArgs<Real>& a, int& blocks_per_pair, bool 
     a.partial = h->partial.as<double>();
     CU(h->prev_match.ensure((size_t)std::max<int64_t>(S.n_total, 1) * sizeof(int)));
     a.match = h->prev_match.as<int>();
+    CU(h->slack.ensure((size_t)std::max<int64_t>(S.n_total, 1) * sizeof(float)));
+    a.slack = nullptr;
     return 0;
 }
 
@@ -533,7 +535,9 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
     CU(cudaStreamSynchronize(st));
     // last iteration's match per source point (bounds the next search); -1 = none yet
     CU(cudaMemsetAsync(h->prev_match.p, 0xFF, (size_t)std::max<int64_t>(h->src.n_total, 1) * sizeof(int), st));
+    CU(cudaMemsetAsync(h->slack.p, 0, (size_t)std::max<int64_t>(h->src.n_total, 1) * sizeof(float), st));
     oa.use_prev = 1;
+    oa.slack = (getenv("GICP_NO_SKIP") && atoi(getenv("GICP_NO_SKIP"))) ? nullptr : h->slack.as<float>();
     SolveArgs sa;
     sa.partial = h->partial.as<double>();
     sa.blocks_per_pair = bpp;
@@ -733,7 +737,7 @@ int gicpDestroy(gicpHandle h) {
     h->src.release();
     h->tgt.release();
     DevBuf* bufs[] = {&h->keys, &h->keys_alt, &h->vals, &h->vals_alt, &h->cub_tmp, &h->cell_count, &h->bbox_part,
-                      &h->knn_idx_tmp, &h->state, &h->partial, &h->red, &h->T_dev, &h->n_active, &h->prev_match, &h->ovf_count, &h->ovf_list};
+                      &h->knn_idx_tmp, &h->state, &h->partial, &h->red, &h->T_dev, &h->n_active, &h->prev_match, &h->slack, &h->ovf_count, &h->ovf_list};
     for (DevBuf* b : bufs) b->release();
     if (h->h_poll) cudaFreeHost(h->h_poll);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);

@@ -42,6 +42,7 @@ template <typename Real> struct ObjArgs {
                                   // correspond_kernel, read by accumulate_kernel; with use_prev the previous
                                   // iteration's match bounds the next search
     int use_prev;
+    float* slack;                 // [n_src_total]: how far a point may still move before its match can change
     const PairState* state;
     const double* T_override;  // optional [n_pairs][(D+1)^2], device
     double* partial;           // [n_pairs][blocks_per_pair][NRED]
@@ -119,9 +120,28 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
         //      that intersect the ball of that radius around p' are searched (still exact). ----
         double bestd = d2cap;
         int bestpos = -1;
+        // Exact skip: at its last search the point's nearest neighbour was d1 away and every other target
+        // point at least d2 away.  While it has moved less than (d2 - d1) / 2 in total since then, the
+        // same target point is still strictly the nearest, so nothing has to be searched.
+        bool skip = false;
         if (a.use_prev) {
             const int pm = a.match[valid ? s : end - 1];
-            if (pm >= 0) {
+            float sl = a.slack ? a.slack[valid ? s : end - 1] : 0.f;
+            if (pm >= 0 && sl > 0.f) {
+                const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
+                double mv2 = 0.0;
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    double v = st.Rp[i * 3 + 0] * px + st.Rp[i * 3 + 1] * py + st.tp[i];
+                    if constexpr (D == 3) v += st.Rp[i * 3 + 2] * pz;
+                    mv2 += (pp[i] - v) * (pp[i] - v);
+                }
+                sl -= __double2float_ru(sqrt(mv2) * (1.0 + 1e-6)) + 1e-30f;
+                skip = sl > 0.f;
+                if (valid && a.slack) a.slack[s] = fmaxf(sl, 0.f);
+            }
+            if (__all_sync(0xffffffffu, skip || !valid)) continue;
+            if (pm >= 0 && !skip) {
                 const PRec<Real> qo = a.tgt_spts[pm];
                 const double e2 = exact_d2((double)qo.x - pp[0], (double)qo.y - pp[1], (double)qo.z - pp[2]);
                 if (e2 <= d2cap) { bestd = e2; bestpos = pm; }
@@ -136,14 +156,24 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
             return fmaf(b, 1.000002f, c1 * sqrtf(b)) + 1e-30f;
         };
         float thr32 = filter_thr(bestd);
+        float m1 = INFINITY, m2 = INFINITY;   // two smallest fp32 squared distances seen (slack of the next iterations)
         auto test = [&](const PRec<Real>& c) {
             bool pass = true;
+            double e2 = 0.0;
             if (sizeof(Real) == 4) {
                 const float dx = (float)c.x - fx, dy = (float)c.y - fy, dz = (float)c.z - fz;
-                pass = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr32;
+                const float d32 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                m2 = fminf(m2, fmaxf(m1, d32));
+                m1 = fminf(m1, d32);
+                pass = d32 <= thr32;
+            } else {
+                e2 = exact_d2((double)c.x - pp[0], (double)c.y - pp[1], (double)c.z - pp[2]);
+                const float d32 = __double2float_rd(e2);
+                m2 = fminf(m2, fmaxf(m1, d32));
+                m1 = fminf(m1, d32);
             }
             if (pass) {
-                const double e2 = exact_d2((double)c.x - pp[0], (double)c.y - pp[1], (double)c.z - pp[2]);
+                if (sizeof(Real) == 4) e2 = exact_d2((double)c.x - pp[0], (double)c.y - pp[1], (double)c.z - pp[2]);
                 const int cpos = (int)c.idx;
                 // exact ties (same float64 distance) go to the lower input index, like the oracle
                 if (e2 < bestd || (e2 == bestd && bestpos >= 0 && cpos != bestpos &&
@@ -166,7 +196,17 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
         const int y0 = max(mylo[1], 0), y1 = min(myhi[1], mt.dims[1] - 1);
         const int z0 = max(mylo[2], 0), z1 = min(myhi[2], mt.dims[2] - 1);
         const int ncell = max(x1 - x0 + 1, 0) * max(y1 - y0 + 1, 0) * max(z1 - z0 + 1, 0);
-        const bool tracked = bestpos >= 0 && ncell <= a.track_max_cells;
+        const bool tracked = !skip && bestpos >= 0 && ncell <= a.track_max_cells;
+        // a tracked lane examines every point of the cell box [mylo, myhi]; everything outside that box is
+        // at least `rad32` away (distance from p' to the nearest box face that has cells behind it)
+        float rad32 = INFINITY;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            if (mylo[i] > 0) rad32 = fminf(rad32, __double2float_rd(pp[i] - (mt.origin[i] + mylo[i] * mt.h)));
+            if (myhi[i] < mt.dims[i] - 1)
+                rad32 = fminf(rad32, __double2float_rd(mt.origin[i] + (myhi[i] + 1) * mt.h - pp[i]));
+        }
+        rad32 = fmaxf(rad32 * 0.999999f - pad, 0.f);
         if (tracked) {
             // ---- phase A: per-lane walk over the (few) cells that intersect the ball ----
             const int* L = a.tgt_lut + mt.lut_base;
@@ -185,7 +225,7 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
         // ---- phase B: warp-cooperative search through the TMA stage.  First the cells the group's
         //      points fall into (a near match shrinks every lane's ball at once), then the rest of
         //      the union box, staging only the blocks that still reach into some lane's ball ----
-        unsigned pending = __ballot_sync(0xffffffffu, !tracked);
+        unsigned pending = __ballot_sync(0xffffffffu, !tracked && !skip);
         if (pending) {
             const int cx = cell_coord(pp[0], mt.origin[0], mt.inv_h);
             const int cy = cell_coord(pp[1], mt.origin[1], mt.inv_h);
@@ -219,10 +259,22 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
                                    window, need);
             }
         }
-        if (!valid) continue;
+        if (!valid || skip) continue;
         const double dist = (bestpos >= 0) ? sqrt(bestd) : INFINITY;
         const bool matched = (bestpos >= 0) && !(dist > a.d_max);  // gicp.py:136 rejects d > d_max
         a.match[s] = matched ? bestpos : -1;
+        if (a.slack) {
+            float sl = 0.f;
+            if (tracked && matched) {
+                // runner-up: at least lb2 away (fp32 error bound of the filter), or outside the examined ball
+                const float d1 = __double2float_ru(dist);
+                const float lb2 = m2 * 0.999999f - c1 * sqrtf(m2);
+                const float d2e = fminf(sqrtf(fmaxf(lb2, 0.f)) * 0.999999f, rad32);
+                sl = fmaxf(0.f, 0.5f * (d2e - d1) * 0.99999f - 1e-6f * (Pf + d1));
+                if (!(m2 < INFINITY)) sl = fmaxf(0.f, 0.5f * (fminf(rad32, 1e30f) - d1) * 0.99999f - 1e-6f * (Pf + d1));
+            }
+            a.slack[s] = sl;
+        }
         if (a.out_idx || a.out_dist) {
             const size_t out_row = (size_t)ms.pt_begin + (size_t)a.src_perm[s];
             if (a.out_idx) a.out_idx[out_row] = matched ? a.tgt_perm[bestpos] : -1;
@@ -293,6 +345,15 @@ __global__ void __launch_bounds__(OBJ_THREADS) accumulate_kernel(const ObjArgs<R
         }
         // ---- W = inv(C_tgt[j] + R C_src[i] R^T), e = q - p' ----
         const PRec<Real> q = a.tgt_spts[bestpos];
+        {   // gicp.py:136: the gate applies to the CURRENT distance (a kept match may have drifted out)
+            const double d2 = exact_d2((double)q.x - pp[0], (double)q.y - pp[1], (double)q.z - pp[2]);
+            if (sqrt(d2) > a.d_max) {
+                if (a.out_W) {
+                    for (int i = 0; i < D * D; ++i) a.out_W[out_row * D * D + i] = 0.0;
+                }
+                continue;
+            }
+        }
         double Cs[NS], M[NS], W[NS], e[D], v[D];
         {
             const Real* cs = a.src_cov + (size_t)s * NS;

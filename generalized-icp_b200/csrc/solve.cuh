@@ -300,6 +300,8 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) solve_kernel(const SolveArgs
                     Rn[i][j] = s;
                 }
         }
+        for (int i = 0; i < 9; ++i) st.Rp[i] = st.R[i];
+        for (int i = 0; i < 3; ++i) st.tp[i] = st.t[i];
         for (int i = 0; i < D; ++i) {
             for (int j = 0; j < D; ++j) st.R[i * 3 + j] = Rn[i][j];
             st.t[i] = tn[i];
@@ -334,6 +336,8 @@ __global__ void init_state_kernel(PairState* state, const double* T0, const doub
         }
         if (D == 2) st.theta = atan2(st.R[3], st.R[0]);
     }
+    for (int i = 0; i < 9; ++i) st.Rp[i] = st.R[i];
+    for (int i = 0; i < 3; ++i) st.tp[i] = st.t[i];
     st.last_loss = INFINITY;
     st.iter = 0;
     st.status = PAIR_ACTIVE;
