@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
 }
 
 template <int D, typename Real>
-__global__ void __launch_bounds__(OBJ_THREADS) accumulate_kernel(const ObjArgs<Real> a) {
+__global__ void __launch_bounds__(OBJ_THREADS, 5) accumulate_kernel(const ObjArgs<Real> a) {
     using DD = Dim<D>;
     using AccT = Real;
     constexpr int NP = DD::NP, NS = DD::NS, NH = DD::NH, NQ = DD::NQ, NRED = DD::NRED;
