@@ -348,7 +348,9 @@ int launch_knn(gicpContext* h, CloudSet& cs, int* d_idx, double* d_dist, cudaStr
         CU(cudaFuncSetAttribute(knn_hist_kernel<D, Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
         CU(cudaFuncSetAttribute(knn_hist_kernel<D, Real>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         const size_t smem_l = (size_t)KNN_WARPS * KNN_LANE_WARP_SMEM;
-        const bool per_lane = getenv("GICP_KNN_COOP") ? atoi(getenv("GICP_KNN_COOP")) == 0 : true;
+        // two equally fast variants (measured): warp-cooperative with TMA-staged cell blocks (default) and
+        // per-lane cell walks from L1 (GICP_KNN_LANE=1)
+        const bool per_lane = getenv("GICP_KNN_LANE") && atoi(getenv("GICP_KNN_LANE")) != 0;
         if (per_lane) {
             CU(cudaFuncSetAttribute(knn_lane_kernel<D, Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
             CU(cudaFuncSetAttribute(knn_lane_kernel<D, Real>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -377,7 +379,7 @@ constexpr size_t OBJ_SMEM = 128 + (size_t)(OBJ_THREADS / 32) * OBJ_STAGE_BYTES;
 double auto_knn_cell(const gicpContext* h) {
     const double r = h->prm.max_distance_nearest_neighbors;
     if (h->prm.knn_cell > 0) return std::max(h->prm.knn_cell, r / 8.0);
-    return 0.4 * r;    // measured optimum of the per-lane fast path on the bench workload (r = 5 m -> 2 m cells)
+    return 0.25 * r;   // measured optimum of the cooperative fast path on the bench workload (r = 5 m -> 1.25 m cells)
 }
 double auto_nn_cell(const gicpContext* h) {
     const double r = h->prm.max_distance_correspondence;

@@ -33,7 +33,8 @@ constexpr int KNN_WARP_SMEM = KNN_STAGE_BYTES + KNN_QUEUE * 32 * 12;
 constexpr int KNN_GROUP_REACH = 4;
 constexpr int KNN_BINS = 64;            // fast path: distance bins per lane (uint8 counters)
 constexpr int KNN_LIST_BYTES = 8192;    // fast path: lane-private candidate list, per warp
-constexpr int KNN_HIST_WARP_SMEM = KNN_STAGE_BYTES + KNN_BINS * 32 + KNN_LIST_BYTES;
+constexpr int KNN_HSTAGE_BYTES = 2048;  // fast cooperative path: small stage, occupancy matters more
+constexpr int KNN_HIST_WARP_SMEM = KNN_HSTAGE_BYTES + KNN_LIST_BYTES;   // histogram aliases the list
 
 template <typename Real> struct KnnArgs {
     const CloudMeta* meta;
@@ -212,10 +213,10 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Rea
     ws.buf = reinterpret_cast<PRec<Real>*>(wbase);
     ws.bar = bars + warp;
     ws.phase = 0;
-    ws.cap = KNN_STAGE_BYTES / (int)sizeof(PRec<Real>);
-    unsigned char* hist = wbase + KNN_STAGE_BYTES;                                  // [KNN_BINS][32] uint8
-    KeyT* lk = reinterpret_cast<KeyT*>(wbase + KNN_STAGE_BYTES + KNN_BINS * 32);    // [CAP][32]
-    int* li = reinterpret_cast<int*>(wbase + KNN_STAGE_BYTES + KNN_BINS * 32 + CAP * 32 * sizeof(KeyT));  // [CAP][32]
+    ws.cap = KNN_HSTAGE_BYTES / (int)sizeof(PRec<Real>);
+    unsigned char* hist = wbase + KNN_HSTAGE_BYTES;                                 // [KNN_BINS][32] uint8, sweep 1
+    KeyT* lk = reinterpret_cast<KeyT*>(wbase + KNN_HSTAGE_BYTES);                   // [CAP][32], sweeps 2-3 (aliases hist)
+    int* li = reinterpret_cast<int*>(wbase + KNN_HSTAGE_BYTES + CAP * 32 * sizeof(KeyT));  // [CAP][32]
 
     const int cloud = blockIdx.y;
     const CloudMeta m = a.meta[cloud];
@@ -224,8 +225,6 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Rea
     const int base = begin + (blockIdx.x * KNN_WARPS + warp) * 32;
     if (base >= end) return;
     if (lane == 0) { mbar_init(ws.bar, 1); mbar_fence_init(); }
-#pragma unroll
-    for (int b = 0; b < KNN_BINS; ++b) hist[b * 32 + lane] = 0;
     __syncwarp();
 
     const bool valid = base + lane < end;
@@ -246,7 +245,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Rea
     float bound32 = r2cap32;   // squared-distance bound under which at least k candidates lie
     float edge_lo = 0.0f;      // lower edge of the histogram bin that holds the k-th candidate
     bool overflow = false;
-    int mcount = 0;
+    const size_t sorted_pos = (size_t)(base + lane);
 
     // fp32 distance of a candidate (float storage), or the float image of the exact one (double storage)
     auto dist32 = [&](const PRec<Real>& c) {
@@ -263,6 +262,10 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Rea
         const unsigned grp = next_group(pending, cx, cy, cz, KNN_GROUP_REACH);
         pending &= ~grp;
         const bool mine = (grp >> lane) & 1u;
+        // the histogram shares its memory with the list of the previous group: start clean
+#pragma unroll
+        for (int b = 0; b < KNN_BINS; ++b) hist[b * 32 + lane] = 0;
+        __syncwarp();
         const int mycell[3] = {cx, cy, cz};
         int qlo[3], qhi[3];
         group_union(grp, lane, mycell, mycell, m, qlo, qhi);
@@ -271,29 +274,32 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Rea
         // ---- sweep 1: histogram the distances ring by ring.  After every ring the histogram bounds
         //      the lane's k-th distance; blocks beyond every lane's bound are not staged ----
         float prov32 = r2cap32;
+        const float lim = mine ? r2cap32 : -1.0f;
         int seen = 0;
         for (int rho = 0; rho <= rho_max; ++rho) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) { lo[c] = max(qlo[c] - rho, 0); hi[c] = min(qhi[c] + rho, m.dims[c] - 1); }
             stream_cells<Real>(m, a.cell_start, a.lut, a.spts, lo, hi, plo, phi, rho > 0, ws, lane,
                                [&](const PRec<Real>* w, int n) {
+                // `lim` is -1 for lanes outside the group, so one compare gates both conditions; the bin index only
+                // needs clamping from below (d2 <= r2cap32 bounds it from above)
                 int j = 0;
                 for (; j + 4 <= n; j += 4) {     // 4 candidates in flight: the histogram update is a dependent chain
                     const PRec<Real> c0 = w[j], c1 = w[j + 1], c2 = w[j + 2], c3 = w[j + 3];
                     const float e0 = dist32(c0), e1 = dist32(c1), e2 = dist32(c2), e3 = dist32(c3);
-                    const int g0 = min(max((int)(__float_as_uint(e0) >> 20) - ubase, 0), KNN_BINS - 1);
-                    const int g1 = min(max((int)(__float_as_uint(e1) >> 20) - ubase, 0), KNN_BINS - 1);
-                    const int g2 = min(max((int)(__float_as_uint(e2) >> 20) - ubase, 0), KNN_BINS - 1);
-                    const int g3 = min(max((int)(__float_as_uint(e3) >> 20) - ubase, 0), KNN_BINS - 1);
-                    if (mine && e0 <= r2cap32) { hist[g0 * 32 + lane] += 1; ++seen; }
-                    if (mine && e1 <= r2cap32) { hist[g1 * 32 + lane] += 1; ++seen; }
-                    if (mine && e2 <= r2cap32) { hist[g2 * 32 + lane] += 1; ++seen; }
-                    if (mine && e3 <= r2cap32) { hist[g3 * 32 + lane] += 1; ++seen; }
+                    const int g0 = max((int)(__float_as_uint(e0) >> 20) - ubase, 0);
+                    const int g1 = max((int)(__float_as_uint(e1) >> 20) - ubase, 0);
+                    const int g2 = max((int)(__float_as_uint(e2) >> 20) - ubase, 0);
+                    const int g3 = max((int)(__float_as_uint(e3) >> 20) - ubase, 0);
+                    if (e0 <= lim) { hist[g0 * 32 + lane] += 1; ++seen; }
+                    if (e1 <= lim) { hist[g1 * 32 + lane] += 1; ++seen; }
+                    if (e2 <= lim) { hist[g2 * 32 + lane] += 1; ++seen; }
+                    if (e3 <= lim) { hist[g3 * 32 + lane] += 1; ++seen; }
                 }
                 for (; j < n; ++j) {
                     const float e0 = dist32(w[j]);
-                    const int g0 = min(max((int)(__float_as_uint(e0) >> 20) - ubase, 0), KNN_BINS - 1);
-                    if (mine && e0 <= r2cap32) { hist[g0 * 32 + lane] += 1; ++seen; }
+                    const int g0 = max((int)(__float_as_uint(e0) >> 20) - ubase, 0);
+                    if (e0 <= lim) { hist[g0 * 32 + lane] += 1; ++seen; }
                 }
             }, [&](int x0, int y0, int z0, int x1, int y1, int z1) {
                 return mine && cell_box_dist2(m, pad, (float)mx, (float)my, (float)mz, x0, y0, z0, x1, y1, z1) <= prov32;
@@ -346,20 +352,20 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Rea
             // only blocks that reach into some lane's ball are staged
             return mine && cell_box_dist2(m, pad, (float)mx, (float)my, (float)mz, x0, y0, z0, x1, y1, z1) <= bound32;
         });
-        if (mine) { mcount = min(cnt_l, CAP); overflow = cnt_l > CAP; }
+        // ---- sweep 3 for this group's lanes (the list memory is recycled by the next group) ----
+        const bool ovf = mine && cnt_l > CAP;
+        overflow = overflow || ovf;
+        if (mine && valid && !ovf)
+            knn_rank_and_finish<D, Real>(a, m, (int)sorted_pos, my_idx, mx, my, mz, lk, li, lane, min(cnt_l, CAP), edge_lo);
         __syncwarp();
     }
-    // hand the whole warp to the general path if any lane's list overflowed
+    // hand the whole warp to the general path if any lane's list overflowed (it recomputes all 32 lanes)
     if (__any_sync(0xffffffffu, overflow)) {
         if (lane == 0) {
             const int slot = atomicAdd(a.overflow_count, 1);
             if (slot < a.overflow_cap) a.overflow_list[slot] = make_int2(cloud, base);
         }
-        return;
     }
-    if (!valid) return;
-
-    knn_rank_and_finish<D, Real>(a, m, base + lane, my_idx, mx, my, mz, lk, li, lane, mcount, edge_lo);
 }
 
 // ================================================================================================
