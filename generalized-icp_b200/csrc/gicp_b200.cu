@@ -773,6 +773,14 @@ int gicpSetSource(gicpHandle h, const void* d_points, const int64_t* h_offsets, 
     return DISPATCH(h, set_cloud, h, GICP_SOURCE, d_points, h_offsets, n_clouds, (cudaStream_t)stream);
 }
 
+int gicpPromoteTargetToSource(gicpHandle h) {
+    if (check(h)) return 1;
+    if (!h->tgt.ready) return fail("no target to promote");
+    std::swap(h->src, h->tgt);   // both sides own the same kind of state (two grids + covariances)
+    h->tgt.ready = false;
+    return 0;
+}
+
 int gicpRegister(gicpHandle h, const double* h_T0, double* d_T, int32_t* d_n_outer, int32_t* d_converged,
                  double* d_loss_hist, double* d_T_hist, int32_t* d_inliers, void* stream) {
     if (check(h)) return 1;

@@ -102,6 +102,14 @@ class GicpEngine:
         """Grid build + covariances of the source(s): gicp.py:111."""
         self._set(SOURCE, points, offsets)
 
+    def promote_target_to_source(self):
+        """Scan sequences: the current target (grids + covariances) becomes the source of the next pair
+        (robot-visualization.py:250-251) without being rebuilt."""
+        _lib.check(self.lib.gicpPromoteTargetToSource(self._h))
+        self._keep[SOURCE] = self._keep.pop(TARGET, None)
+        self._n[SOURCE] = self._n[TARGET]
+        self._n[TARGET] = (0, 0)
+
     # ---- the loop ----
     def register(self, T0=None, history=True) -> RegistrationResult:
         n_pairs = self._n[SOURCE][1]

@@ -76,6 +76,12 @@ int gicpSetParams(gicpHandle h, const gicpParams* p);
 int gicpSetTarget(gicpHandle h, const void* d_points, const int64_t* h_offsets, int32_t n_clouds, void* stream);
 int gicpSetSource(gicpHandle h, const void* d_points, const int64_t* h_offsets, int32_t n_clouds, void* stream);
 
+/* Scan sequences (robot-visualization.py:246-252: "source <- target; target <- current scan"): the
+ * target of pair k is the source of pair k+1, so its grids and covariances are reused instead of
+ * being rebuilt (the reference recomputes both on every call, gicp.py:104,111).  After this call
+ * the handle's source is the former target; set a new target with gicpSetTarget.             */
+int gicpPromoteTargetToSource(gicpHandle h);
+
 /* ---- the registration loop (replaces gicp.py:107-174) ------------------------------------
  * Runs all pairs to convergence / max_iterations on the device.
  *  h_T0        optional (n_clouds, dim+1, dim+1) initial transforms (NULL = identity, gicp.py:107)

@@ -262,3 +262,35 @@ def test_edge_cases(torch_cuda):
     assert np.array_equal(one["src_cov0"][0], np.eye(2))
     with pytest.raises(Exception):
         compat.gicp_extended(np.zeros((3, 4)), np.zeros((3, 4)))
+
+
+# ------------------------------------------------------------------------------------------------
+# streaming scan-sequence odometry (grid + covariance reuse)
+# ------------------------------------------------------------------------------------------------
+def test_scan_sequence_reuse_is_bit_identical(torch_cuda):
+    """Promoting the target to the next pair's source gives bit-identical transforms to registering
+    every pair from scratch through the drop-in gicp(), and the integrated pose follows the
+    simulated robot (robot-visualization.py:258-265)."""
+    from generalized_icp_b200 import compat, synthetic
+    from generalized_icp_b200.odometry import ScanOdometry, integrate_pose, trajectory_errors
+    scans, truth = synthetic.lidar_sequence(seed=2, num_rays=360, n_scans=14)
+    odo = ScanOdometry(start_pose=(50.0, 400.0, 0.0))
+    for s in scans:
+        odo.push(s)
+    assert len(odo.transforms) == len(scans) - 1
+    pose = (50.0, 400.0, 0.0)
+    for i in range(len(scans) - 1):
+        r = compat.gicp_extended(np.asarray(scans[i]), np.asarray(scans[i + 1]), max_distance_nearest_neighbors=200,
+                                 tolerance=1, full_history=False)
+        assert np.array_equal(r["T"], odo.transforms[i])
+        assert r["n_outer"] == odo.iterations[i]
+        pose = integrate_pose(pose, r["T"])
+    assert np.allclose(pose, odo.pose)
+    # the first scan is taken after 5 ticks of driving: compare displacements from the first pose
+    est = np.asarray(odo.poses)
+    tru = np.asarray(truth)
+    est_rel = est - est[0]
+    tru_rel = tru - tru[0]
+    err = trajectory_errors(est_rel + [0, 0, 0], np.column_stack([tru_rel[:, 0], tru_rel[:, 1], tru_rel[:, 2]]))
+    assert err["position_max"] < 25.0          # px, after 13 pairs of ~10 px steps with +-2 px range noise
+    assert err["orientation_max"] < 0.2
