@@ -481,6 +481,7 @@ int objective_args(gicpContext* h, ObjArgs<Real>& a, int& blocks_per_pair, bool 
     a.ignore_status = 0;
     a.track_max_cells = getenv("GICP_TRACK_CELLS") ? atoi(getenv("GICP_TRACK_CELLS")) : 1 << 30;
     a.centre_first = getenv("GICP_CENTRE_FIRST") ? atoi(getenv("GICP_CENTRE_FIRST")) : 1;
+    a.shell_search = getenv("GICP_SHELL_SEARCH") ? atoi(getenv("GICP_SHELL_SEARCH")) : 1;
     int span = S.max_n;
     if (allow_slice && h->comm && S.n_clouds == 1) {
         a.slice_begin = (int)(S.n_total * h->rank / h->n_ranks);

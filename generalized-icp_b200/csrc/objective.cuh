@@ -56,6 +56,7 @@ template <typename Real> struct ObjArgs {
     int ignore_status;
     int track_max_cells;      // per-lane walk only when the ball spans at most this many cells
     int centre_first;
+    int shell_search;         // untracked lanes search per-lane shells before the cooperative phase
 };
 
 template <int D, typename Real>
@@ -222,10 +223,52 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
                 }
             }
         }
-        // ---- phase B: warp-cooperative search through the TMA stage.  First the cells the group's
-        //      points fall into (a near match shrinks every lane's ball at once), then the rest of
-        //      the union box, staging only the blocks that still reach into some lane's ball ----
-        unsigned pending = __ballot_sync(0xffffffffu, !tracked && !skip);
+        // ---- phase A': lanes without a usable previous match (first iteration, gated-out points) search
+        //      shell by shell around their own cell; every hit shrinks the ball, cells beyond it are
+        //      skipped, and the search stops as soon as the searched box covers the best distance ----
+        bool shell_done = tracked || skip;
+        if (a.shell_search && !shell_done) {
+            const int scx = cell_coord(pp[0], mt.origin[0], mt.inv_h);
+            const int scy = cell_coord(pp[1], mt.origin[1], mt.inv_h);
+            const int scz = (D == 3) ? cell_coord(pp[2], mt.origin[2], mt.inv_h) : 0;
+            const int* L = a.tgt_lut + mt.lut_base;
+            auto shell_cell = [&](int x, int y, int z) {
+                if (x < 0 || y < 0 || z < 0 || x >= mt.dims[0] || y >= mt.dims[1] || z >= mt.dims[2]) return;
+                if (cell_box_dist2(mt, pad, fx, fy, fz, x, y, z, x, y, z) > thr32) return;
+                const int* cs = a.tgt_cell_start + mt.cell_base +
+                                (__ldg(L + x) | __ldg(L + GICP_LUT_N + y) | __ldg(L + 2 * GICP_LUT_N + z));
+                const int j0 = __ldg(cs), j1 = __ldg(cs + 1);
+                for (int j = j0; j < j1; ++j) test(a.tgt_spts[j]);
+            };
+            constexpr int ZR = (D == 3) ? 1 : 0;
+            const int sc[3] = {scx, scy, scz};
+            for (int rho = 0; rho <= 2; ++rho) {
+                for (int dz = -rho * ZR; dz <= rho * ZR; ++dz)
+                    for (int dy = -rho; dy <= rho; ++dy) {
+                        const bool outer = abs(dz) == rho || abs(dy) == rho;
+                        if (outer) {
+                            for (int dx = -rho; dx <= rho; ++dx) shell_cell(scx + dx, scy + dy, scz + dz);
+                        } else {
+                            shell_cell(scx - rho, scy + dy, scz + dz);
+                            shell_cell(scx + rho, scy + dy, scz + dz);
+                        }
+                    }
+                // distance from p' to the nearest face of the searched box that has cells behind it
+                double cover = INFINITY;
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    if (sc[i] - rho > 0) cover = fmin(cover, pp[i] - (mt.origin[i] + (sc[i] - rho) * mt.h));
+                    if (sc[i] + rho < mt.dims[i] - 1) cover = fmin(cover, mt.origin[i] + (sc[i] + rho + 1) * mt.h - pp[i]);
+                }
+                cover *= (1.0 - 1e-9);
+                if ((bestpos >= 0 && bestd <= cover * cover) || cover >= a.d_max) { shell_done = true; break; }
+            }
+        }
+        // ---- phase B: warp-cooperative search through the TMA stage (what the shells could not settle).
+        //      First the cells the group's points fall into (a near match shrinks every lane's ball at
+        //      once), then the rest of the union box, staging only the blocks that still reach into some
+        //      lane's ball ----
+        unsigned pending = __ballot_sync(0xffffffffu, !shell_done);
         if (pending) {
             const int cx = cell_coord(pp[0], mt.origin[0], mt.inv_h);
             const int cy = cell_coord(pp[1], mt.origin[1], mt.inv_h);
