@@ -26,6 +26,7 @@ constexpr int OBJ_THREADS = 128;
 constexpr int OBJ_STAGE_BYTES = 2048;  // per warp (small: occupancy matters more than window size here)
 constexpr int OBJ_GROUP_REACH = 4;
 constexpr int OBJ_TRACK_MAX_CELLS = 8;
+constexpr int OBJ_MAX_PPT = 16;
 
 template <typename Real> struct ObjArgs {
     const CloudMeta* src_meta;
@@ -99,12 +100,59 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
     if (lane == 0) { mbar_init(ws.bar, 1); mbar_fence_init(); }
     __syncwarp();
 
-    for (int it = 0; it < a.ppt; ++it) {
-        const int wbase = begin + (blockIdx.x * a.ppt + it) * OBJ_THREADS + warp * 32;
-        if (wbase >= end) break;  // warp-uniform
-        const int s = wbase + lane;
-        const bool valid = s < end;
-        const PRec<Real> p = a.src_spts[valid ? s : end - 1];
+    // ---- pass 1 (tracking iterations): decide for every point of the block whether its match can have
+    //      changed at all, and compact the ones that need a search into a dense work list, so that the
+    //      search below runs with full warps instead of a few busy lanes per warp.
+    //      Exact skip: at its last search the point's nearest neighbour was d1 away and every other
+    //      target point at least d2 away.  While it has moved less than (d2 - d1) / 2 in total since
+    //      then, the same target point is still strictly the nearest. ----
+    __shared__ int s_list[OBJ_THREADS * OBJ_MAX_PPT];
+    __shared__ int s_count;
+    const int blk_begin = begin + blockIdx.x * a.ppt * OBJ_THREADS;
+    const int blk_end = min(end, blk_begin + a.ppt * OBJ_THREADS);
+    const bool compact = a.use_prev && a.slack != nullptr;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    if (compact) {
+        for (int sbase = blk_begin + warp * 32; sbase < blk_end; sbase += OBJ_THREADS) {
+            const int s = sbase + lane;
+            bool need_search = false;
+            if (s < blk_end) {
+                need_search = true;
+                const int pm = a.match[s];
+                float sl = a.slack[s];
+                if (pm >= 0 && sl > 0.f) {
+                    const PRec<Real> p = a.src_spts[s];
+                    const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
+                    double mv2 = 0.0;
+#pragma unroll
+                    for (int i = 0; i < D; ++i) {
+                        double vn = R[i][0] * px + R[i][1] * py + t[i];
+                        double vo = st.Rp[i * 3 + 0] * px + st.Rp[i * 3 + 1] * py + st.tp[i];
+                        if constexpr (D == 3) { vn += R[i][2] * pz; vo += st.Rp[i * 3 + 2] * pz; }
+                        mv2 += (vn - vo) * (vn - vo);
+                    }
+                    sl -= __double2float_ru(sqrt(mv2) * (1.0 + 1e-6)) + 1e-30f;
+                    a.slack[s] = fmaxf(sl, 0.f);
+                    need_search = !(sl > 0.f);
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, need_search);
+            int wpos = 0;
+            if (lane == 0 && bal) wpos = atomicAdd(&s_count, __popc(bal));
+            wpos = __shfl_sync(0xffffffffu, wpos, 0);
+            if (need_search) s_list[wpos + __popc(bal & ((1u << lane) - 1u))] = s;
+        }
+        __syncthreads();
+    }
+    const int n_work = compact ? s_count : max(blk_end - blk_begin, 0);
+
+    for (int w0 = warp * 32; w0 < n_work; w0 += OBJ_THREADS) {   // warp-uniform
+        const bool valid = w0 + lane < n_work;
+        const int wi = valid ? w0 + lane : n_work - 1;
+        const int s = compact ? s_list[wi] : blk_begin + wi;
+        constexpr bool skip = false;
+        const PRec<Real> p = a.src_spts[s];
         double pp[3] = {0.0, 0.0, 0.0};  // p' = R p + t (gicp.py:119)
         {
             const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
@@ -121,28 +169,9 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
         //      that intersect the ball of that radius around p' are searched (still exact). ----
         double bestd = d2cap;
         int bestpos = -1;
-        // Exact skip: at its last search the point's nearest neighbour was d1 away and every other target
-        // point at least d2 away.  While it has moved less than (d2 - d1) / 2 in total since then, the
-        // same target point is still strictly the nearest, so nothing has to be searched.
-        bool skip = false;
         if (a.use_prev) {
-            const int pm = a.match[valid ? s : end - 1];
-            float sl = a.slack ? a.slack[valid ? s : end - 1] : 0.f;
-            if (pm >= 0 && sl > 0.f) {
-                const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
-                double mv2 = 0.0;
-#pragma unroll
-                for (int i = 0; i < D; ++i) {
-                    double v = st.Rp[i * 3 + 0] * px + st.Rp[i * 3 + 1] * py + st.tp[i];
-                    if constexpr (D == 3) v += st.Rp[i * 3 + 2] * pz;
-                    mv2 += (pp[i] - v) * (pp[i] - v);
-                }
-                sl -= __double2float_ru(sqrt(mv2) * (1.0 + 1e-6)) + 1e-30f;
-                skip = sl > 0.f;
-                if (valid && a.slack) a.slack[s] = fmaxf(sl, 0.f);
-            }
-            if (__all_sync(0xffffffffu, skip || !valid)) continue;
-            if (pm >= 0 && !skip) {
+            const int pm = a.match[s];
+            if (pm >= 0) {
                 const PRec<Real> qo = a.tgt_spts[pm];
                 const double e2 = exact_d2((double)qo.x - pp[0], (double)qo.y - pp[1], (double)qo.z - pp[2]);
                 if (e2 <= d2cap) { bestd = e2; bestpos = pm; }
