@@ -360,7 +360,8 @@ int launch_knn(gicpContext* h, CloudSet& cs, int* d_idx, double* d_dist, cudaStr
         }
         const dim3 lgrid(296, 1);
         if (a.k <= 6) KNN_LAUNCH(6, lgrid, 1);
-        else KNN_LAUNCH(20, lgrid, 1);
+        else if (a.k <= 20) KNN_LAUNCH(20, lgrid, 1);
+        else KNN_LAUNCH(32, lgrid, 1);
         h->launches += 2;
     } else {
         if (a.k <= 6) KNN_LAUNCH(6, grid, 0);
