@@ -430,8 +430,18 @@ __global__ void __launch_bounds__(OBJ_THREADS, 5) accumulate_kernel(const ObjArg
         {
             const Real* cs = a.src_cov + (size_t)s * NS;
             const Real* ct = a.tgt_cov + (size_t)bestpos * NS;
+            if constexpr (sizeof(Real) == 4 && NS == 6) {
+                // 24-byte records, 8-byte aligned: three 64-bit loads each instead of six 32-bit ones
+                const float2* c2 = reinterpret_cast<const float2*>(cs);
+                const float2* t2 = reinterpret_cast<const float2*>(ct);
+                const float2 s0 = __ldg(c2), s1 = __ldg(c2 + 1), s2 = __ldg(c2 + 2);
+                const float2 u0 = __ldg(t2), u1 = __ldg(t2 + 1), u2 = __ldg(t2 + 2);
+                Cs[0] = s0.x; Cs[1] = s0.y; Cs[2] = s1.x; Cs[3] = s1.y; Cs[4] = s2.x; Cs[5] = s2.y;
+                M[0] = u0.x; M[1] = u0.y; M[2] = u1.x; M[3] = u1.y; M[4] = u2.x; M[5] = u2.y;
+            } else {
 #pragma unroll
-            for (int i = 0; i < NS; ++i) { Cs[i] = (double)cs[i]; M[i] = (double)ct[i]; }
+                for (int i = 0; i < NS; ++i) { Cs[i] = (double)cs[i]; M[i] = (double)ct[i]; }
+            }
         }
         if constexpr (D == 3) {
             const double C[3][3] = {{Cs[0], Cs[1], Cs[2]}, {Cs[1], Cs[3], Cs[4]}, {Cs[2], Cs[4], Cs[5]}};
