@@ -26,7 +26,7 @@ class GicpParams(C.Structure):
         ("lambda_tangent", C.c_double),
         ("lambda_normal", C.c_double),
         ("inner_max_iterations", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("covariance_model", C.c_int32),
         ("knn_cell", C.c_double),
         ("nn_cell", C.c_double),
         ("max_cells_per_cloud", C.c_int64),

@@ -36,7 +36,8 @@ def _engine(dim, storage):
 
 def gicp_extended(source_points, target_points, max_iterations=100, tolerance=1e-6,
                   max_distance_correspondence=150, max_distance_nearest_neighbors=50, k=6,
-                  lambda_tangent=100.0, lambda_normal=10.0, storage="f64", full_history=True, **engine_params):
+                  lambda_tangent=100.0, lambda_normal=10.0, storage="f64", full_history=True, covariance_model=0,
+                  **engine_params):
     """The registration with everything the engine knows (SURVEY.md discrepancy 3: the reference
     computes ``min_loss`` and drops it; here the loss history, inlier counts and the fitness-like
     final loss are returned as well).  Returns a dict."""
@@ -53,7 +54,8 @@ def gicp_extended(source_points, target_points, max_iterations=100, tolerance=1e
     eng.set_params(k=k, max_iterations=int(max_iterations), tolerance=float(tolerance),
                    max_distance_correspondence=float(max_distance_correspondence),
                    max_distance_nearest_neighbors=float(max_distance_nearest_neighbors),
-                   lambda_tangent=float(lambda_tangent), lambda_normal=float(lambda_normal), **engine_params)
+                   lambda_tangent=float(lambda_tangent), lambda_normal=float(lambda_normal),
+                   covariance_model=int(covariance_model), **engine_params)
     np_dtype = np.float64 if storage == "f64" else np.float32
     s_dev = torch.as_tensor(np.ascontiguousarray(src[:, :dim], dtype=np_dtype), device=eng.device)
     t_dev = torch.as_tensor(np.ascontiguousarray(tgt[:, :dim], dtype=np_dtype), device=eng.device)

@@ -262,6 +262,16 @@ __global__ void regather_cov_kernel(const CloudMeta* __restrict__ meta, const in
     for (int i = 0; i < NS; ++i) cov_dst[(size_t)s * NS + i] = cov_src[(size_t)ss * NS + i];
 }
 
+// ICP variants: a side whose covariance is a constant multiple of the identity (0 or 1) skips K2
+template <int D, typename Real>
+__global__ void fill_cov_kernel(Real* __restrict__ cov, size_t n, Real diag) {
+    constexpr int NS = Dim<D>::NS;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int a = 0, k = 0; a < D; ++a)
+        for (int b = a; b < D; ++b, ++k) cov[i * NS + k] = (a == b) ? diag : Real(0);
+}
+
 template <int D, typename Real>
 __global__ void export_cov_kernel(const CloudMeta* __restrict__ meta, const PRec<Real>* __restrict__ spts,
                                   const Real* __restrict__ cov_sorted, double* __restrict__ out) {
@@ -431,8 +441,17 @@ int set_cloud(gicpContext* h, int which, const void* d_points, const int64_t* h_
         slice_e = (int)std::min<int64_t>(n, per * (h->rank + 1));
         CU(cs.cov_knn.ensure((size_t)per * h->n_ranks * ns_of(D) * sizeof(Real)));
     }
-    if (launch_knn<D, Real>(h, cs, nullptr, nullptr, st, slice_b, slice_e)) return 1;
-    if (sharded) {
+    // covariance model (ICP family): GICP estimates both sides; point-to-point uses C_src = 0, C_tgt = I;
+    // point-to-plane uses C_src = 0 and the estimated target covariances
+    const int model = h->prm.covariance_model;
+    const bool constant = (model == GICP_POINT_TO_POINT) || (model == GICP_POINT_TO_PLANE && which == GICP_SOURCE);
+    if (constant) {
+        const Real diag = (model == GICP_POINT_TO_POINT && which == GICP_TARGET) ? Real(1) : Real(0);
+        const size_t n = (size_t)std::max<int64_t>(cs.n_total, 1);
+        fill_cov_kernel<D, Real><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cs.cov_knn.as<Real>(), n, diag);
+        h->launches += 1;
+    } else if (launch_knn<D, Real>(h, cs, nullptr, nullptr, st, slice_b, slice_e)) return 1;
+    if (sharded && !constant) {
         const size_t bytes = (size_t)per * ns_of(D) * sizeof(Real);
         char* basep = cs.cov_knn.as<char>();
         int rc = g_nccl.AllGather(basep + bytes * h->rank, basep, bytes, NCCL_INT8, h->comm, st);
@@ -756,6 +775,7 @@ int gicpSetParams(gicpHandle h, const gicpParams* p) {
     if (p->max_iterations < 1) return fail("max_iterations must be >= 1");
     if (!(p->max_distance_nearest_neighbors > 0)) return fail("max_distance_nearest_neighbors must be > 0");
     if (!(p->max_distance_correspondence > 0)) return fail("max_distance_correspondence must be > 0");
+    if (p->covariance_model < 0 || p->covariance_model > 2) return fail("covariance_model must be 0, 1 or 2");
     h->prm = *p;
     if (h->prm.inner_max_iterations <= 0) h->prm.inner_max_iterations = 50;
     h->src.ready = false;

@@ -39,6 +39,7 @@ typedef struct gicpContext* gicpHandle;
 
 enum { GICP_STORAGE_F32 = 0, GICP_STORAGE_F64 = 1 };
 enum { GICP_SOURCE = 0, GICP_TARGET = 1 };
+enum { GICP_PLANE_TO_PLANE = 0, GICP_POINT_TO_POINT = 1, GICP_POINT_TO_PLANE = 2 };
 
 /* Parameters; names follow gicp.py:78 where the reference has them. */
 typedef struct gicpParams {
@@ -50,7 +51,9 @@ typedef struct gicpParams {
     double  lambda_tangent;       /* gicp.py:5   epsilon = 100                                            */
     double  lambda_normal;        /* gicp.py:11  epsilon * 0.1 = 10                                       */
     int32_t inner_max_iterations; /* LM iterations of the on-device inner solve (replaces fmin_cg, :152)  */
-    int32_t reserved0;
+    int32_t covariance_model;     /* ICP family through the same kernels (presentation/main.typ:446-462):
+                                   * 0 plane-to-plane = GICP (the reference), 1 point-to-point (C_A = 0, C_B = I),
+                                   * 2 point-to-plane (C_A = 0, C_B = the target's surface-aligned covariance)    */
     double  knn_cell;             /* uniform-grid cell edge for the k-NN grid; 0 = auto (radius / 2)      */
     double  nn_cell;              /* cell edge of the target's 1-NN grid;      0 = auto (d_max / 2)       */
     int64_t max_cells_per_cloud;  /* cell-table budget per cloud; 0 = auto                                */

@@ -354,7 +354,7 @@ def rotvec_from_matrix(R):
 def gicp_oracle(source_points, target_points, max_iterations=100, tolerance=1e-6,
                 max_distance_correspondence=150, max_distance_nearest_neighbors=50,
                 k=K_DEFAULT, lam_t=LAMBDA_TANGENT, lam_n=LAMBDA_NORMAL,
-                inner="newton", recompute_src_cov=True, knn="kdtree", record=True):
+                inner="newton", recompute_src_cov=True, knn="kdtree", record=True, covariance_model=0):
     """Restatement of gicp.py:78-174, any dimension d in {2,3}.
 
     inner = "cg"     fidelity (fmin_cg, gicp.py:152)
@@ -362,6 +362,9 @@ def gicp_oracle(source_points, target_points, max_iterations=100, tolerance=1e-6
     recompute_src_cov: True  = gicp.py:120 (k-NN covariances of the transformed
                                cloud every iteration),
                        False = the R_k C_0 R_k^T shortcut the engine uses.
+    covariance_model: 0 = plane-to-plane (GICP, the reference), 1 = point-to-point (C_src = 0, C_tgt = I),
+                      2 = point-to-plane (C_src = 0, C_tgt estimated) - the slides' generalisation table
+                      (presentation/main.typ:446-462); 1 and 2 imply the R C R^T shortcut (C_src = 0).
     Returns a dict; ``T``/``all_T``/... mirror the reference's 7-tuple
     (gicp.py:174) and ``trace`` holds the per-iteration stage data used for
     teacher-forced parity tests."""
@@ -375,6 +378,11 @@ def gicp_oracle(source_points, target_points, max_iterations=100, tolerance=1e-6
     offset = np.zeros(nparam)
     last = np.inf
     src_cov0, src_knn = compute_covariances(src, max_distance_nearest_neighbors, k, lam_t, lam_n, knn)
+    if covariance_model in (1, 2):
+        src_cov0 = np.zeros_like(src_cov0)
+        recompute_src_cov = False
+        if covariance_model == 1:
+            tgt_cov = np.broadcast_to(np.eye(dim), tgt_cov.shape).copy()
     hw_src, hw_tgt, all_src_cov, trace = [], [], [], []
     converged_at = None
     for it in range(max_iterations):

@@ -374,3 +374,21 @@ def test_duplicate_points_tie_break(torch_cuda):
     nn, _, _ = eng.correspond(np.eye(3), with_W=False)
     want_nn, _ = O.correspond(pts, pts, 5.0, method="brute")
     assert np.array_equal(nn.cpu().numpy(), want_nn)
+
+
+# ------------------------------------------------------------------------------------------------
+# ICP-family variants through the same kernels (only the covariance model changes)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("model", [1, 2])
+def test_icp_variants_vs_oracle(model, torch_cuda):
+    from generalized_icp_b200 import compat
+    from oracle import gicp_oracle as O
+    src, tgt, _ = _pair3(4)
+    r = compat.gicp_extended(src, tgt, storage="f64", full_history=False, covariance_model=model, **P3)
+    ref = O.gicp_oracle(src, tgt, inner="newton", record=False, covariance_model=model, **P3)
+    assert r["n_outer"] == ref["n_outer"]
+    dR = r["T"][:3, :3].T @ ref["T"][:3, :3]
+    assert np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1)) <= 1e-5
+    assert np.linalg.norm(r["T"][:3, 3] - ref["T"][:3, 3]) <= 1e-5 * 30.0
+    if model == 1:
+        assert np.array_equal(r["tgt_cov"][0], np.eye(3)) and not r["src_cov0"].any()
