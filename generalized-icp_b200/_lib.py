@@ -11,7 +11,7 @@ SYMBOLS = [
     "gicpCreate", "gicpDestroy", "gicpGetLastError", "gicpVersion", "gicpDefaultParams", "gicpSetParams",
     "gicpSetTarget", "gicpSetSource", "gicpPromoteTargetToSource", "gicpRegister", "gicpKnn", "gicpCovariances", "gicpCorrespond",
     "gicpNormalEquations", "gicpSourceCovariancesAt", "gicpCommGetUniqueId", "gicpCommInit", "gicpCommDestroy",
-    "gicpLaunchCount", "gicpProfile", "gicpProfileRead",
+    "gicpLaunchCount", "gicpProfile", "gicpProfileRead", "gicpRayCast",
 ]
 
 
@@ -65,6 +65,7 @@ def load():
     lib.gicpCommDestroy.argtypes = [vp]
     lib.gicpLaunchCount.argtypes = [vp]
     lib.gicpLaunchCount.restype = i64
+    lib.gicpRayCast.argtypes = [C.c_int, vp, i32, i32, vp, i32, vp, i32, C.c_double, vp, vp, vp, vp]
     lib.gicpProfile.argtypes = [vp, C.c_int]
     lib.gicpProfileRead.argtypes = [vp, dp, C.POINTER(i64)]
     _lib = lib

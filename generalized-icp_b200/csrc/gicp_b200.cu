@@ -16,6 +16,7 @@
 #include "grid.cuh"
 #include "knn_cov.cuh"
 #include "objective.cuh"
+#include "raycast.cuh"
 #include "solve.cuh"
 
 using namespace gicp;
@@ -870,6 +871,19 @@ int gicpCommDestroy(gicpHandle h) {
     h->comm = nullptr;
     h->n_ranks = 1;
     h->rank = 0;
+    return 0;
+}
+
+int gicpRayCast(int device, const double* d_poses, int32_t n_poses, int32_t num_rays, const double* d_segments,
+                int32_t n_seg, const double* d_circles, int32_t n_circ, double max_range, const double* d_noise,
+                double* d_rel_xy, int32_t* d_hit, void* stream) {
+    if (n_poses <= 0 || num_rays <= 0 || 360 % num_rays != 0) return fail("need n_poses > 0 and num_rays dividing 360");
+    if (!d_poses || !d_rel_xy || !d_hit) return fail("null pointer");
+    CU(cudaSetDevice(device));
+    RayCastArgs a{d_poses, n_poses, num_rays, d_segments, n_seg, d_circles, n_circ, max_range, d_noise, d_rel_xy, d_hit};
+    const long long n = (long long)n_poses * num_rays;
+    raycast_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+    CU(cudaGetLastError());
     return 0;
 }
 

@@ -234,3 +234,34 @@ def reduced_form_loss(red, dim, T_lin, T_eval):
                 for dd in range(d):
                     quad += Z[cc, a] * Z[dd, b] * Hq[sym(NP, a, b), sym(d, cc, dd)]
     return float(c - 2.0 * np.sum(G * Z) + quad)
+
+
+def ray_cast(poses, num_rays=90, obstacles=None, max_range=400.0, noise=None, device=None):
+    """Batched LiDAR scans on the device (robot-visualization.py:42-120, 222-237).
+    poses: (n, 3) x, y, yaw_deg.  obstacles: list of (x, y, w, h) rectangles and (cx, cy, r) circles - default
+    = the demo's world (robot-visualization.py:35-40).  noise: optional (n, num_rays) additive range noise.
+    Returns (rel_xy (n, num_rays, 2) f64, hit (n, num_rays) bool) as device tensors."""
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+    if obstacles is None:
+        obstacles = [(100, 250, 200, 50), (400, 450, 50, 200), (600, 300, 50), (200, 550, 75)]
+    segs, circs = [], []
+    for ob in obstacles:
+        if len(ob) == 4:
+            x, y, w, h = ob
+            tl, tr, bl, br = (x, y), (x + w, y), (x, y + h), (x + w, y + h)
+            for p3, p4 in ((tl, tr), (tr, br), (br, bl), (bl, tl)):          # robot-visualization.py:52-57
+                segs.append([*p3, *p4])
+        else:
+            circs.append(list(ob))
+    poses_t = torch.as_tensor(np.asarray(poses, dtype=np.float64), device=dev).contiguous()
+    n = poses_t.shape[0]
+    seg_t = torch.as_tensor(np.asarray(segs, dtype=np.float64).reshape(-1, 4), device=dev)
+    circ_t = torch.as_tensor(np.asarray(circs, dtype=np.float64).reshape(-1, 3), device=dev)
+    noise_t = None if noise is None else torch.as_tensor(np.asarray(noise, dtype=np.float64), device=dev).contiguous()
+    rel = torch.empty((n, num_rays, 2), dtype=torch.float64, device=dev)
+    hit = torch.empty((n, num_rays), dtype=torch.int32, device=dev)
+    _lib.check(lib.gicpRayCast(dev.index, _ptr(poses_t), n, num_rays, _ptr(seg_t), seg_t.shape[0], _ptr(circ_t),
+                               circ_t.shape[0], float(max_range), _ptr(noise_t), _ptr(rel), _ptr(hit),
+                               C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return rel, hit.bool()

@@ -133,6 +133,15 @@ int gicpCommGetUniqueId(char id[128]);
 int gicpCommInit(gicpHandle h, int32_t n_ranks, int32_t rank, const char id[128]);
 int gicpCommDestroy(gicpHandle h);
 
+/* ---- input generation for scan-sequence benchmarks: the robot demo's 2-D LiDAR ray caster ------
+ * (robot-visualization.py:42-120 cast_ray, :222-237 scan loop), one thread per ray, all poses at once.
+ *  d_poses (n_poses, 3) f64: x, y, yaw in degrees;  d_segments (n_seg, 4) f64: x3, y3, x4, y4;
+ *  d_circles (n_circ, 3) f64: cx, cy, r;  d_noise optional (n_poses, num_rays) f64 additive range noise;
+ *  d_rel_xy (n_poses, num_rays, 2) f64 robot-relative hit points;  d_hit (n_poses, num_rays) i32.     */
+int gicpRayCast(int device, const double* d_poses, int32_t n_poses, int32_t num_rays, const double* d_segments,
+                int32_t n_seg, const double* d_circles, int32_t n_circ, double max_range, const double* d_noise,
+                double* d_rel_xy, int32_t* d_hit, void* stream);
+
 /* number of kernels this library launched on this handle since creation (bench bookkeeping) */
 int64_t gicpLaunchCount(gicpHandle h);
 

@@ -392,3 +392,45 @@ def test_icp_variants_vs_oracle(model, torch_cuda):
     assert np.linalg.norm(r["T"][:3, 3] - ref["T"][:3, 3]) <= 1e-5 * 30.0
     if model == 1:
         assert np.array_equal(r["tgt_cov"][0], np.eye(3)) and not r["src_cov0"].any()
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU LiDAR ray caster vs the headless restatement of robot-visualization.py:42-120
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("num_rays", [90, 360])
+def test_ray_caster_matches_demo(num_rays, torch_cuda):
+    import math
+    import random
+    from generalized_icp_b200 import synthetic
+    from generalized_icp_b200.engine import ray_cast
+    sim = synthetic.LidarSim(seed=0, num_rays=num_rays)
+    poses, want, noises = [], [], []
+    for step in range(25):
+        sim.step(up=True, right=(step % 7 == 3), left=(step % 11 == 5))
+        poses.append((sim.x, sim.y, sim.yaw))
+        # replay cast_ray with a recorded noise stream so the device gets the same numbers
+        rec = []
+        class Rec(random.Random):
+            def uniform(self, a, b):
+                v = super().uniform(a, b)
+                rec.append(v)
+                return v
+        sim.rnd = Rec(1000 + step)
+        rows, nz = [], []
+        for angle in range(sim.yaw, sim.yaw + 360, 360 // num_rays):
+            before = len(rec)
+            d = sim.cast_ray(angle)
+            nz.append(rec[-1] if len(rec) > before else 0.0)
+            if d:
+                rows.append((d * math.cos(math.radians(angle - sim.yaw)), d * math.sin(math.radians(angle - sim.yaw))))
+            else:
+                rows.append(None)
+        want.append(rows)
+        noises.append(nz)
+    rel, hit = ray_cast(np.asarray(poses, dtype=np.float64), num_rays=num_rays, noise=np.asarray(noises))
+    rel, hit = rel.cpu().numpy(), hit.cpu().numpy()
+    for i, rows in enumerate(want):
+        for j, r in enumerate(rows):
+            assert bool(hit[i, j]) == (r is not None), (i, j)
+            if r is not None:
+                assert abs(rel[i, j, 0] - r[0]) < 1e-9 and abs(rel[i, j, 1] - r[1]) < 1e-9
