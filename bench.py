@@ -269,7 +269,7 @@ def run_b200(args):
     try:
         cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.startswith("traffic_"))
         tj = json.load(open(os.path.join(ROOT, "profiles", cands[-1])))
-        kname = {"knn_cov": "knn_lane_kernel", "correspond": "correspond_kernel", "accumulate": "accumulate_kernel"}[dom]
+        kname = {"knn_cov": "knn_hist_kernel", "correspond": "correspond_kernel", "accumulate": "accumulate_kernel"}[dom]
         per_pt = sum(tj["launches"][kname]) / len(tj["launches"][kname]) / tj["points_per_launch"]
         units = kernels[dom]["launches"]
         pts_per_launch = (pts_rank / 2) if dom == "knn_cov" else iters_sum * args.points / max(1, units)
