@@ -130,6 +130,56 @@ class GicpEngine:
                                          _ptr(inl), self._stream()))
         return RegistrationResult(T, n_outer, conv, loss, T_hist, inl)
 
+    def register_host_batch(self, h_src, h_tgt, offsets, chunk_pairs=1024, history=False):
+        """Batches that live in (pinned) HOST memory: pairs are registered in chunks, and the host->device
+        copy of chunk i+1 runs on a second stream while chunk i is being registered, so the PCIe transfer
+        hides behind the compute.  h_src / h_tgt: (n_total, dim) CPU tensors (pin them for real overlap),
+        offsets: (n_pairs + 1,) row offsets shared by both sides.  Returns (T (P, d+1, d+1), n_outer (P,),
+        converged_at (P,)) as pinned host tensors."""
+        off = np.asarray(offsets, dtype=np.int64)
+        n_pairs = len(off) - 1
+        d1 = self.dim + 1
+        T_out = torch.empty((n_pairs, d1, d1), dtype=torch.float64, pin_memory=True)
+        n_out = torch.empty((n_pairs,), dtype=torch.int32, pin_memory=True)
+        c_out = torch.empty((n_pairs,), dtype=torch.int32, pin_memory=True)
+        chunks = [(a, min(a + chunk_pairs, n_pairs)) for a in range(0, n_pairs, chunk_pairs)]
+        rows = max(int(off[b] - off[a]) for a, b in chunks)
+        if getattr(self, "_hb_rows", 0) < rows:
+            self._hb = [(torch.empty((rows, self.dim), dtype=self.dtype, device=self.device),
+                         torch.empty((rows, self.dim), dtype=self.dtype, device=self.device)) for _ in range(2)]
+            self._hb_rows = rows
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+
+        def upload(i):
+            a, b = chunks[i]
+            r0, r1 = int(off[a]), int(off[b])
+            ds, dt = self._hb[i % 2]
+            self._copy_stream.wait_stream(main)       # the buffer's previous user (chunk i-2) is done
+            with torch.cuda.stream(self._copy_stream):
+                ds[:r1 - r0].copy_(h_src[r0:r1], non_blocking=True)
+                dt[:r1 - r0].copy_(h_tgt[r0:r1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            return ev
+
+        ev = upload(0)
+        for i, (a, b) in enumerate(chunks):
+            r0, r1 = int(off[a]), int(off[b])
+            ds, dt = self._hb[i % 2]
+            main.wait_event(ev)
+            if i + 1 < len(chunks):
+                ev = upload(i + 1)                    # in flight while this chunk is registered
+            loc = off[a:b + 1] - off[a]
+            self.set_target(dt[:r1 - r0], loc)
+            self.set_source(ds[:r1 - r0], loc)
+            r = self.register(history=history)
+            T_out[a:b].copy_(r.T, non_blocking=True)
+            n_out[a:b].copy_(r.n_outer, non_blocking=True)
+            c_out[a:b].copy_(r.converged_at, non_blocking=True)
+        torch.cuda.synchronize(self.device)
+        return T_out, n_out, c_out
+
     # ---- stage entry points ----
     def knn(self, which, with_dist=True):
         n = self._n[which][0]

@@ -434,3 +434,23 @@ def test_ray_caster_matches_demo(num_rays, torch_cuda):
             assert bool(hit[i, j]) == (r is not None), (i, j)
             if r is not None:
                 assert abs(rel[i, j, 0] - r[0]) < 1e-9 and abs(rel[i, j, 1] - r[1]) < 1e-9
+
+
+def test_register_host_batch_matches_device_batch(torch_cuda):
+    """The chunked, copy-overlapped host-batch path returns exactly what one device-resident batch returns."""
+    torch = torch_cuda
+    from generalized_icp_b200.engine import GicpEngine
+    pairs = [_pair3(s, n=1200 + 100 * s) for s in range(5)]
+    S = np.concatenate([p[0] for p in pairs])
+    T = np.concatenate([p[1] for p in pairs])
+    off = np.concatenate([[0], np.cumsum([len(p[0]) for p in pairs])])
+    eng = GicpEngine(3, "f32")
+    eng.set_params(**P3)
+    eng.set_target(torch.as_tensor(T, device="cuda"), off)
+    eng.set_source(torch.as_tensor(S, device="cuda"), off)
+    r = eng.register()
+    hS, hT = torch.as_tensor(S).pin_memory(), torch.as_tensor(T).pin_memory()
+    T_h, n_h, c_h = eng.register_host_batch(hS, hT, off, chunk_pairs=2)
+    assert np.array_equal(T_h.numpy(), r.T.cpu().numpy())
+    assert np.array_equal(n_h.numpy(), r.n_outer.cpu().numpy())
+    assert np.array_equal(c_h.numpy(), r.converged_at.cpu().numpy())
