@@ -99,11 +99,11 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-// make the barrier's initialisation visible to the async proxy (the TMA unit) of this CTA.
-// (fence.mbarrier_init.release.cluster would also do, but it compiles to CCTL.IVALL - a full L1D
-// invalidation per warp start - and nothing here is shared across a cluster.)
+// make the barrier's initialisation visible to the async proxy (the TMA unit): the documented pattern
+// (CUTLASS fence_barrier_init).  A lighter fence.proxy.async was tried; it measured no faster and one bench
+// run in ~10 died with "unspecified launch failure" while it was in, so the documented fence stays.
 __device__ __forceinline__ void mbar_fence_init() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
