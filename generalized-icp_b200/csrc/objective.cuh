@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
 }
 
 template <int D, typename Real>
-__global__ void __launch_bounds__(OBJ_THREADS, 5) accumulate_kernel(const ObjArgs<Real> a) {
+__global__ void __launch_bounds__(OBJ_THREADS, 4) accumulate_kernel(const ObjArgs<Real> a) {
     using DD = Dim<D>;
     using AccT = Real;
     constexpr int NP = DD::NP, NS = DD::NS, NH = DD::NH, NQ = DD::NQ, NRED = DD::NRED;
@@ -393,10 +393,46 @@ __global__ void __launch_bounds__(OBJ_THREADS, 5) accumulate_kernel(const ObjArg
     double loss_acc = 0.0;
     int cnt = 0;
 
+    // software pipeline over the thread's points: while point `it` is being processed, the gather of
+    // point it+1 (target record + covariance, addressed by its match) and the match index of point it+2
+    // are already in flight - the kernel is bound by dependent-load latency otherwise
+    const int s_first = begin + blockIdx.x * a.ppt * OBJ_THREADS + threadIdx.x;
+    auto load_match = [&](int it) {
+        const int s = s_first + it * OBJ_THREADS;
+        return (it < a.ppt && s < end) ? a.match[s] : -1;
+    };
+    struct Gathered { PRec<Real> q; Real ct[NS]; };
+    auto gather = [&](int m) {
+        Gathered g;
+        if (m >= 0) {
+            g.q = a.tgt_spts[m];
+            const Real* ct = a.tgt_cov + (size_t)m * NS;
+            if constexpr (sizeof(Real) == 4 && NS == 6) {
+                const float2* t2 = reinterpret_cast<const float2*>(ct);
+                const float2 u0 = __ldg(t2), u1 = __ldg(t2 + 1), u2 = __ldg(t2 + 2);
+                g.ct[0] = u0.x; g.ct[1] = u0.y; g.ct[2] = u1.x; g.ct[3] = u1.y; g.ct[4] = u2.x; g.ct[5] = u2.y;
+            } else {
+#pragma unroll
+                for (int i = 0; i < NS; ++i) g.ct[i] = ct[i];
+            }
+        } else {
+            g.q.x = g.q.y = g.q.z = Real(0); g.q.idx = 0;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) g.ct[i] = Real(0);
+        }
+        return g;
+    };
+    int m_cur = load_match(0);
+    Gathered g_cur = gather(m_cur);
+    int m_next = load_match(1);
     for (int it = 0; it < a.ppt; ++it) {
-        const int s = begin + (blockIdx.x * a.ppt + it) * OBJ_THREADS + threadIdx.x;
+        const int s = s_first + it * OBJ_THREADS;
         if (s >= end) break;
-        const int bestpos = a.match[s];
+        const int bestpos = m_cur;
+        const Gathered g = g_cur;
+        g_cur = gather(m_next);           // in flight during this iteration's arithmetic
+        m_cur = m_next;
+        m_next = load_match(it + 2);
         const size_t out_row = (size_t)ms.pt_begin + (size_t)(a.out_W ? a.src_perm[s] : 0);
         if (bestpos < 0) {
             if (a.out_W) {
@@ -416,7 +452,7 @@ __global__ void __launch_bounds__(OBJ_THREADS, 5) accumulate_kernel(const ObjArg
             }
         }
         // ---- W = inv(C_tgt[j] + R C_src[i] R^T), e = q - p' ----
-        const PRec<Real> q = a.tgt_spts[bestpos];
+        const PRec<Real> q = g.q;
         {   // gicp.py:136: the gate applies to the CURRENT distance (a kept match may have drifted out)
             const double d2 = exact_d2((double)q.x - pp[0], (double)q.y - pp[1], (double)q.z - pp[2]);
             if (sqrt(d2) > a.d_max) {
@@ -429,19 +465,17 @@ __global__ void __launch_bounds__(OBJ_THREADS, 5) accumulate_kernel(const ObjArg
         double Cs[NS], M[NS], W[NS], e[D], v[D];
         {
             const Real* cs = a.src_cov + (size_t)s * NS;
-            const Real* ct = a.tgt_cov + (size_t)bestpos * NS;
             if constexpr (sizeof(Real) == 4 && NS == 6) {
-                // 24-byte records, 8-byte aligned: three 64-bit loads each instead of six 32-bit ones
+                // 24-byte records, 8-byte aligned: three 64-bit loads instead of six 32-bit ones
                 const float2* c2 = reinterpret_cast<const float2*>(cs);
-                const float2* t2 = reinterpret_cast<const float2*>(ct);
                 const float2 s0 = __ldg(c2), s1 = __ldg(c2 + 1), s2 = __ldg(c2 + 2);
-                const float2 u0 = __ldg(t2), u1 = __ldg(t2 + 1), u2 = __ldg(t2 + 2);
                 Cs[0] = s0.x; Cs[1] = s0.y; Cs[2] = s1.x; Cs[3] = s1.y; Cs[4] = s2.x; Cs[5] = s2.y;
-                M[0] = u0.x; M[1] = u0.y; M[2] = u1.x; M[3] = u1.y; M[4] = u2.x; M[5] = u2.y;
             } else {
 #pragma unroll
-                for (int i = 0; i < NS; ++i) { Cs[i] = (double)cs[i]; M[i] = (double)ct[i]; }
+                for (int i = 0; i < NS; ++i) Cs[i] = (double)cs[i];
             }
+#pragma unroll
+            for (int i = 0; i < NS; ++i) M[i] = (double)g.ct[i];
         }
         if constexpr (D == 3) {
             const double C[3][3] = {{Cs[0], Cs[1], Cs[2]}, {Cs[1], Cs[3], Cs[4]}, {Cs[2], Cs[4], Cs[5]}};
