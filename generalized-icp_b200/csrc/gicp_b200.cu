@@ -127,10 +127,9 @@ struct gicpContext {
     int device = 0, dim = 2, storage = GICP_STORAGE_F64;
     gicpParams prm;
     CloudSet src, tgt;
-    DevBuf keys, keys_alt, vals, vals_alt, cub_tmp, cell_count, bbox_part, knn_idx_tmp;
+    DevBuf keys, keys_alt, vals, vals_alt, cub_tmp, cell_count, bbox_part;
     DevBuf state, partial, red, T_dev, n_active, prev_match, slack, ovf_count, ovf_list;
     int* h_poll = nullptr;  // pinned
-    cudaEvent_t poll_event = nullptr;
     int64_t launches = 0;
     // per-stage CUDA-event timing (off by default): stage ids in include/gicp_b200.h
     bool prof_on = false;
@@ -761,7 +760,7 @@ int gicpDestroy(gicpHandle h) {
     h->src.release();
     h->tgt.release();
     DevBuf* bufs[] = {&h->keys, &h->keys_alt, &h->vals, &h->vals_alt, &h->cub_tmp, &h->cell_count, &h->bbox_part,
-                      &h->knn_idx_tmp, &h->state, &h->partial, &h->red, &h->T_dev, &h->n_active, &h->prev_match, &h->slack, &h->ovf_count, &h->ovf_list};
+                      &h->state, &h->partial, &h->red, &h->T_dev, &h->n_active, &h->prev_match, &h->slack, &h->ovf_count, &h->ovf_list};
     for (DevBuf* b : bufs) b->release();
     if (h->h_poll) cudaFreeHost(h->h_poll);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);

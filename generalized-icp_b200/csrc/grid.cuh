@@ -166,9 +166,4 @@ __global__ void morton_lut_kernel(const CloudMeta* __restrict__ meta, int* __res
     lut[m.lut_base + e] = code;
 }
 
-__global__ void offsets_to_int_kernel(const long long* __restrict__ in, int* __restrict__ out, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (int)in[i];
-}
-
 }  // namespace gicp

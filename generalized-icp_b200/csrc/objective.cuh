@@ -25,7 +25,6 @@ namespace gicp {
 constexpr int OBJ_THREADS = 128;
 constexpr int OBJ_STAGE_BYTES = 2048;  // per warp (small: occupancy matters more than window size here)
 constexpr int OBJ_GROUP_REACH = 4;
-constexpr int OBJ_TRACK_MAX_CELLS = 8;
 constexpr int OBJ_MAX_PPT = 16;
 
 template <typename Real> struct ObjArgs {
