@@ -912,3 +912,4 @@ int gicpProfileRead(gicpHandle h, double ms_out[GICP_N_STAGES], int64_t count_ou
 }
 
 }  // extern "C"
+

@@ -97,6 +97,28 @@ __device__ __forceinline__ void regularised_cov(const double S[6], bool ident, d
     }
 }
 
+// moments about the query point (count, sum of offsets, sum of outer products) -> sample covariance
+// (ddof = 1) -> regularised covariance of sorted position s
+template <int D, typename Real>
+__device__ __forceinline__ void knn_finish_cov(const KnnArgs<Real>& a, int s, int n_valid, const double mean[3],
+                                               double S[6]) {
+    constexpr int NS = Dim<D>::NS;
+    double C[NS];
+    const bool ident = n_valid <= 1;     // gicp.py:27,33-34
+    if (!ident) {
+        const double inv = 1.0 / n_valid;
+        const double m0 = mean[0] * inv, m1 = mean[1] * inv, m2 = mean[2] * inv;
+        const double f = 1.0 / (n_valid - 1);   // ddof = 1 (np.cov default, gicp.py:12)
+        S[0] = (S[0] - n_valid * m0 * m0) * f; S[1] = (S[1] - n_valid * m0 * m1) * f;
+        S[2] = (S[2] - n_valid * m0 * m2) * f; S[3] = (S[3] - n_valid * m1 * m1) * f;
+        S[4] = (S[4] - n_valid * m1 * m2) * f; S[5] = (S[5] - n_valid * m2 * m2) * f;
+    }
+    regularised_cov<D>(S, ident, a.lam_t, a.lam_n, C);
+    Real* out = a.cov_sorted + (size_t)s * NS;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) out[i] = (Real)C[i];
+}
+
 // sweep 3 of the fast paths: rank a lane's candidate list by counting, accumulate the moments of the
 // winners (rank < k, inside the radius), write the optional index/distance outputs and the
 // regularised covariance of sorted position s.
@@ -105,7 +127,6 @@ __device__ __forceinline__ void knn_rank_and_finish(const KnnArgs<Real>& a, cons
                                                     Real mx, Real my, Real mz, const Real* lk, const int* li,
                                                     int lane, int mcount, float edge_lo) {
     using KeyT = Real;
-    constexpr int NS = Dim<D>::NS;
     // ---- sweep 3: rank the list by counting; winners (rank < k) go to their sorted slot ----
     const size_t cloud_row0 = (size_t)m.pt_begin;
     auto exact_key = [&](int idx) {
@@ -181,20 +202,7 @@ __device__ __forceinline__ void knn_rank_and_finish(const KnnArgs<Real>& a, cons
             if (out_d) out_d[o] = INFINITY;
         }
     }
-    double C[NS];
-    const bool ident = n_valid <= 1;     // gicp.py:27,33-34
-    if (!ident) {
-        const double inv = 1.0 / n_valid;
-        const double m0 = mean[0] * inv, m1 = mean[1] * inv, m2 = mean[2] * inv;
-        const double f = 1.0 / (n_valid - 1);   // ddof = 1 (np.cov default, gicp.py:12)
-        S[0] = (S[0] - n_valid * m0 * m0) * f; S[1] = (S[1] - n_valid * m0 * m1) * f;
-        S[2] = (S[2] - n_valid * m0 * m2) * f; S[3] = (S[3] - n_valid * m1 * m1) * f;
-        S[4] = (S[4] - n_valid * m1 * m2) * f; S[5] = (S[5] - n_valid * m2 * m2) * f;
-    }
-    regularised_cov<D>(S, ident, a.lam_t, a.lam_n, C);
-    Real* out = a.cov_sorted + (size_t)s * NS;
-#pragma unroll
-    for (int i = 0; i < NS; ++i) out[i] = (Real)C[i];
+    knn_finish_cov<D, Real>(a, s, n_valid, mean, S);
 }
 
 // ================================================================================================
@@ -204,7 +212,6 @@ template <int D, typename Real>
 __global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Real> a) {
     using KeyT = Real;  // list key: the fp32 filter distance (float storage) / the exact key (double storage)
     constexpr int CAP = knn_list_cap<Real>();
-    constexpr int NS = Dim<D>::NS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -379,7 +386,6 @@ template <int D, typename Real>
 __global__ void __launch_bounds__(KNN_THREADS) knn_lane_kernel(const KnnArgs<Real> a) {
     using KeyT = Real;
     constexpr int CAP = knn_list_cap<Real>();
-    constexpr int NS = Dim<D>::NS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* wbase = smem_raw + warp * KNN_LANE_WARP_SMEM;
@@ -543,17 +549,10 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_lane_kernel(const KnnArgs<Rea
 // ================================================================================================
 template <int D, typename Real, int KCAP>
 __device__ __forceinline__ void knn_general_chunk(const KnnArgs<Real>& a, int cloud, int base, int end,
-                                                  unsigned char* wbase, uint64_t* bar, int lane) {
-    WarpStage<Real> ws;
-    ws.buf = reinterpret_cast<PRec<Real>*>(wbase);
-    ws.bar = bar;
-    ws.phase = 0;
-    ws.cap = KNN_STAGE_BYTES / (int)sizeof(PRec<Real>);
+                                                  unsigned char* wbase, WarpStage<Real>& ws, int lane) {
     double* qd = reinterpret_cast<double*>(wbase + KNN_STAGE_BYTES);                 // [KNN_QUEUE][32]
     int* qi = reinterpret_cast<int*>(wbase + KNN_STAGE_BYTES + KNN_QUEUE * 32 * 8);  // [KNN_QUEUE][32]
     const CloudMeta m = a.meta[cloud];
-    if (lane == 0) { mbar_init(ws.bar, 1); mbar_fence_init(); }
-    __syncwarp();
 
     const bool valid = base + lane < end;
     const PRec<Real> me = a.spts[valid ? base + lane : end - 1];
@@ -744,13 +743,21 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_general_kernel(const KnnArgs<
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* wbase = smem_raw + 128 + warp * KNN_WARP_SMEM;
+    // one mbarrier per warp for the whole kernel: the phase carries over from chunk to chunk
+    WarpStage<Real> ws;
+    ws.buf = reinterpret_cast<PRec<Real>*>(wbase);
+    ws.bar = bars + warp;
+    ws.phase = 0;
+    ws.cap = KNN_STAGE_BYTES / (int)sizeof(PRec<Real>);
+    if (lane == 0) { mbar_init(ws.bar, 1); mbar_fence_init(); }
+    __syncwarp();
     if (!from_list) {
         const CloudMeta m = a.meta[blockIdx.y];
         int begin = m.pt_begin, end = m.pt_end;
         if (a.slice_begin >= 0) { begin = max(begin, a.slice_begin); end = min(end, a.slice_end); }
         const int base = begin + (blockIdx.x * KNN_WARPS + warp) * 32;
         if (base >= end) return;
-        knn_general_chunk<D, Real, KCAP>(a, blockIdx.y, base, end, wbase, bars + warp, lane);
+        knn_general_chunk<D, Real, KCAP>(a, blockIdx.y, base, end, wbase, ws, lane);
     } else {
         const int n = min(*a.overflow_count, a.overflow_cap);
         for (int e = blockIdx.x * KNN_WARPS + warp; e < n; e += gridDim.x * KNN_WARPS) {
@@ -758,7 +765,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_general_kernel(const KnnArgs<
             const CloudMeta m = a.meta[it.x];
             int end = m.pt_end;
             if (a.slice_begin >= 0) end = min(end, a.slice_end);
-            knn_general_chunk<D, Real, KCAP>(a, it.x, it.y, end, wbase, bars + warp, lane);
+            knn_general_chunk<D, Real, KCAP>(a, it.x, it.y, end, wbase, ws, lane);
             __syncwarp();
         }
     }
