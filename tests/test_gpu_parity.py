@@ -352,6 +352,35 @@ def test_knn_paths_bit_exact(dim, storage, k, radius, n, torch_cuda):
     assert np.array_equal(cov[cnt <= 1], np.broadcast_to(np.eye(dim), (int((cnt <= 1).sum()), dim, dim)))
 
 
+def test_knn_overflow_many_chunks_per_warp(torch_cuda):
+    """More overflow chunks than the hand-over kernel has warps (296 x 4): every warp of the general
+    path then serves several chunks in a row on the same TMA stage and mbarrier."""
+    torch = torch_cuda
+    from generalized_icp_b200 import synthetic
+    from generalized_icp_b200.engine import GicpEngine
+    from oracle import gicp_oracle as O
+    n, k, radius = 48_000, 6, 400.0     # 1500 chunks, all of them overflow (radius >> spacing)
+    pts, _, _ = synthetic.patches3d_pair(n=n, n_patches=8, cube=60.0, patch=30.0, seed=11)
+    dev_pts = torch.as_tensor(pts, device="cuda").float()
+    cloud = dev_pts.double().cpu().numpy()
+    eng = GicpEngine(3, "f32")
+    eng.set_params(k=k, max_distance_nearest_neighbors=radius, max_distance_correspondence=radius)
+    eng.set_target(dev_pts)
+    idx, dist = eng.knn(1)
+    want, wantd = O.knn_kdtree(cloud, k, radius)
+    got = idx.cpu().numpy()
+    # cKDTree breaks exact distance ties arbitrarily: compare the distances everywhere, the indices
+    # where the neighbour distances are distinct
+    d = dist.cpu().numpy()
+    assert np.abs(d - wantd).max() < 1e-9 * radius
+    distinct = (np.diff(wantd, axis=1) > 0).all(1)
+    assert distinct.mean() > 0.99
+    assert np.array_equal(got[distinct], want[distinct])
+    cov = eng.covariances(1).cpu().numpy()
+    ev = np.linalg.eigvalsh(cov)
+    assert np.isfinite(cov).all() and ev.min() > 0.99 and ev.max() < 100.01
+
+
 def test_duplicate_points_tie_break(torch_cuda):
     """Exact ties (duplicated points) go to the lower index, like the canonical oracle rule."""
     torch = torch_cuda
