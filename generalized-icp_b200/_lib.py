@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgicp_b200.so")
+# GICP_B200_LIB: another build of the same library (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("GICP_B200_LIB") or os.path.join(_HERE, "libgicp_b200.so")
 
 # every symbol include/gicp_b200.h declares
 SYMBOLS = [
