@@ -120,7 +120,7 @@ def run_reference(args):
             "config": config_json(args, cfg, prm, args.gpus),
             "cpu_baseline": {"value": cps, "unit": UNIT, "cores": d["cores"], "kind": "port", "sample": sample},
             "e2e": {"value": cps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -180,7 +180,6 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
     cfg, prm = workload_config(args)
@@ -344,13 +343,31 @@ def run_b200(args):
                 "data": "synthetic", "pairs_per_sec": pairs_per_s, "config": config_json(args, cfg, prm, n_gpus),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_all), "roofline": roofline,
                 "cpu_baseline": cpu, "accuracy": acc}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: whatever a library prints to fd 1 (NCCL's version banner)
+    is sent to stderr, the line itself is written to the descriptor stdout had at start-up."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
     args = parse()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
