@@ -149,31 +149,12 @@ __device__ __forceinline__ void knn_rank_and_finish(const KnnArgs<Real>& a, cons
     int n_sure = 0;
     for (int j = 0; j < mcount; ++j) n_sure += ((float)lk[j * 32 + lane] < sure_thr) ? 1 : 0;
     if (n_sure >= a.k) sure_thr = -1.0f;   // only possible if an 8-bit histogram counter wrapped: rank everything
-    // list entry i is one of the k nearest, at rank r (the rank only matters for the index output)
-    auto take = [&](int ii, int r) {
-        const Real* q = a.raw + (cloud_row0 + ii) * D;
-        const double d0 = (double)q[0] - (double)mx, d1 = (double)q[1] - (double)my;
-        const double d2 = (D == 3) ? (double)q[D - 1] - (double)mz : 0.0;
-        const double dist = sqrt(exact_d2(d0, d1, d2));
-        const bool ok = dist < a.radius;         // exclusive bound, gicp.py:24
-        if (ok) {
-            ++n_valid;
-            // moments about the query point keep the scatter matrix accurate
-            mean[0] += d0; mean[1] += d1; mean[2] += d2;
-            S[0] += d0 * d0; S[1] += d0 * d1; S[2] += d0 * d2;
-            S[3] += d1 * d1; S[4] += d1 * d2; S[5] += d2 * d2;
-        }
-        if (out_idx) {
-            out_idx[r] = ok ? ii : -1;
-            if (out_d) out_d[r] = ok ? dist : INFINITY;
-        }
-    };
-    // pass A: the sure entries are taken as they come; the entries that need ranking are only marked.
+    // pass A: the sure entries are selected as they come; the entries that need ranking are only marked.
     // (Ranking them inside this loop would run every lane's counting loop on its own - the marked
     // positions differ from lane to lane - at a few active lanes per instruction.)
-    unsigned amb = 0;
+    unsigned amb = 0, sel = 0;
     for (int i = 0; i < mcount; ++i) {
-        if ((float)lk[i * 32 + lane] < sure_thr) take(li[i * 32 + lane], 0);
+        if ((float)lk[i * 32 + lane] < sure_thr) sel |= 1u << i;
         else amb |= 1u << i;
     }
     // pass B: every lane ranks its next marked entry by counting, all lanes side by side
@@ -205,7 +186,40 @@ __device__ __forceinline__ void knn_rank_and_finish(const KnnArgs<Real>& a, cons
         } else {
             for (int j = 0; j < mcount; ++j) r += key_less((double)lk[j * 32 + lane], li[j * 32 + lane], (double)ki, ii) ? 1 : 0;
         }
-        if (r < a.k) take(ii, r);
+        if (r < a.k) {
+            sel |= 1u << i;
+            if (out_idx) {   // index output: every entry comes through here (sure_thr = -1)
+                const double dist = sqrt(exact_key(ii));
+                const bool ok = dist < a.radius;
+                out_idx[r] = ok ? ii : -1;
+                if (out_d) out_d[r] = ok ? dist : INFINITY;
+            }
+        }
+    }
+    // pass C: moments of the selected entries, in list order; the coordinates of the next one are
+    // fetched (a random 12-byte gather) while the current one is accumulated
+    {
+        auto fetch = [&](unsigned mask, Real& x, Real& y, Real& z) {
+            const Real* q = a.raw + (cloud_row0 + li[(__ffs(mask) - 1) * 32 + lane]) * D;
+            x = q[0]; y = q[1]; z = (D == 3) ? q[D - 1] : Real(0);
+        };
+        Real nx = 0, ny = 0, nz = 0;
+        if (sel) fetch(sel, nx, ny, nz);
+        while (sel) {
+            const Real qx = nx, qy = ny, qz = nz;
+            sel &= sel - 1;
+            if (sel) fetch(sel, nx, ny, nz);
+            const double d0 = (double)qx - (double)mx, d1 = (double)qy - (double)my;
+            const double d2 = (D == 3) ? (double)qz - (double)mz : 0.0;
+            const double dist = sqrt(exact_d2(d0, d1, d2));
+            if (dist < a.radius) {         // exclusive bound, gicp.py:24
+                ++n_valid;
+                // moments about the query point keep the scatter matrix accurate
+                mean[0] += d0; mean[1] += d1; mean[2] += d2;
+                S[0] += d0 * d0; S[1] += d0 * d1; S[2] += d0 * d2;
+                S[3] += d1 * d1; S[4] += d1 * d2; S[5] += d2 * d2;
+            }
+        }
     }
     if (out_idx) {
         for (int o = min(mcount, a.k); o < a.k; ++o) {
