@@ -33,7 +33,9 @@ constexpr int KNN_WARP_SMEM = KNN_STAGE_BYTES + KNN_QUEUE * 32 * 12;
 constexpr int KNN_GROUP_REACH = 4;
 constexpr int KNN_BINS = 64;            // fast path: distance bins per lane (uint8 counters)
 constexpr int KNN_LIST_BYTES = 8192;    // fast path: lane-private candidate list, per warp
-constexpr int KNN_HSTAGE_BYTES = 2048;  // fast cooperative path: small stage, occupancy matters more
+// fast cooperative path: 1 KB stage + 8 KB list per warp = 37 KB per block -> 6 blocks (24 warps) per SM at the
+// kernel's 80 registers; measured 24.8 ms (1 KB) / 26.7 (2 KB, 5 blocks) / 25.9 (512 B) per 2 x 256 clouds
+constexpr int KNN_HSTAGE_BYTES = 1024;
 constexpr int KNN_HIST_WARP_SMEM = KNN_HSTAGE_BYTES + KNN_LIST_BYTES;   // histogram aliases the list
 
 template <typename Real> struct KnnArgs {
