@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Rea
         // ---- sweep 1: histogram the distances ring by ring.  After every ring the histogram bounds
         //      the lane's k-th distance; blocks beyond every lane's bound are not staged ----
         float prov32 = r2cap32;
-        const float lim = mine ? r2cap32 : -1.0f;
+        float lim = mine ? r2cap32 : -1.0f;   // candidates beyond the lane's provisional bound are not binned
         int seen = 0;
         for (int rho = 0; rho <= rho_max; ++rho) {
 #pragma unroll
@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Rea
             // every candidate of bins <= kb has d2 < edge2 (exact: bin edges are float bit patterns)
             const float edge2 = have ? __uint_as_float((unsigned)(ubase + kb + 1) << 20) : r2cap32;
             prov32 = fminf(prov32, edge2);
+            if (mine) lim = prov32;
             if (rho == 0) continue;
             const double cover = rho * m.h * (1.0 - 1e-9);
             const bool mine_done = !mine || (have && (double)prov32 <= cover * cover);
