@@ -371,17 +371,28 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Rea
         // ---- sweep 2: keep the candidates under the bound ----
         const int none[3] = {0, 0, 0};
         int cnt_l = 0;
+        const float lim2 = mine ? bound32 : -1.0f;
         stream_cells<Real>(m, a.cell_start, a.lut, a.spts, lo, hi, none, none, false, ws, lane,
                            [&](const PRec<Real>* w, int n) {
-            for (int j = 0; j < n; ++j) {
-                const PRec<Real> c = w[j];
-                KeyT key;
-                if (sizeof(Real) == 4) key = (KeyT)dist32(c);
-                else key = (KeyT)exact_d2((double)c.x - (double)mx, (double)c.y - (double)my, (double)c.z - (double)mz);
-                if (mine && (float)key <= bound32) {
+            auto key_of = [&](const PRec<Real>& c) -> KeyT {
+                if (sizeof(Real) == 4) return (KeyT)dist32(c);
+                return (KeyT)exact_d2((double)c.x - (double)mx, (double)c.y - (double)my, (double)c.z - (double)mz);
+            };
+            auto keep = [&](KeyT key, const PRec<Real>& c) {
+                if ((float)key <= lim2) {
                     if (cnt_l < CAP) { lk[cnt_l * 32 + lane] = key; li[cnt_l * 32 + lane] = (int)c.idx; }
                     ++cnt_l;
                 }
+            };
+            int j = 0;
+            for (; j + 4 <= n; j += 4) {     // 4 candidates in flight (shared-memory load latency)
+                const PRec<Real> c0 = w[j], c1 = w[j + 1], c2 = w[j + 2], c3 = w[j + 3];
+                const KeyT k0 = key_of(c0), k1 = key_of(c1), k2 = key_of(c2), k3 = key_of(c3);
+                keep(k0, c0); keep(k1, c1); keep(k2, c2); keep(k3, c3);
+            }
+            for (; j < n; ++j) {
+                const PRec<Real> c = w[j];
+                keep(key_of(c), c);
             }
         }, [&](int x0, int y0, int z0, int x1, int y1, int z1) {
             // only blocks that reach into some lane's ball are staged
