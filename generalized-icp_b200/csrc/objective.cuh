@@ -212,6 +212,17 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
                 }
             }
         };
+        // the points of one cell, the next record already in flight while the current one is tested
+        auto run_cell = [&](int j0, int j1) {
+            if (j0 >= j1) return;
+            PRec<Real> c = a.tgt_spts[j0];
+            for (int j = j0 + 1; j < j1; ++j) {
+                const PRec<Real> nx = a.tgt_spts[j];
+                test(c);
+                c = nx;
+            }
+            test(c);
+        };
         const double rad = sqrt(bestd) * (1.0 + 1e-9) + 1e-300;
         int mylo[3], myhi[3];
 #pragma unroll
@@ -246,7 +257,7 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
                     for (int x = x0; x <= x1; ++x) {
                         const int* cs = a.tgt_cell_start + mt.cell_base + (lyz | __ldg(L + x));
                         const int j0 = __ldg(cs), j1 = __ldg(cs + 1);
-                        for (int j = j0; j < j1; ++j) test(a.tgt_spts[j]);
+                        run_cell(j0, j1);
                     }
                 }
             }
@@ -266,7 +277,7 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
                 const int* cs = a.tgt_cell_start + mt.cell_base +
                                 (__ldg(L + x) | __ldg(L + GICP_LUT_N + y) | __ldg(L + 2 * GICP_LUT_N + z));
                 const int j0 = __ldg(cs), j1 = __ldg(cs + 1);
-                for (int j = j0; j < j1; ++j) test(a.tgt_spts[j]);
+                run_cell(j0, j1);
             };
             constexpr int ZR = (D == 3) ? 1 : 0;
             const int sc[3] = {scx, scy, scz};
