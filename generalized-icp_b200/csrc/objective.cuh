@@ -411,9 +411,23 @@ __global__ void __launch_bounds__(OBJ_THREADS, 4) accumulate_kernel(const ObjArg
         const int s = s_first + it * OBJ_THREADS;
         return (it < a.ppt && s < end) ? a.match[s] : -1;
     };
-    struct Gathered { PRec<Real> q; Real ct[NS]; };
-    auto gather = [&](int m) {
+    struct Gathered { PRec<Real> q; Real ct[NS]; PRec<Real> p; Real cs[NS]; };
+    auto gather = [&](int m, int it) {
         Gathered g;
+        {   // the source side of the same point: streamed, but just as far away as the gathered target
+            const int s = min(s_first + it * OBJ_THREADS, end - 1);
+            g.p = a.src_spts[s];
+            const Real* cs = a.src_cov + (size_t)s * NS;
+            if constexpr (sizeof(Real) == 4 && NS == 6) {
+                // 24-byte records, 8-byte aligned: three 64-bit loads instead of six 32-bit ones
+                const float2* c2 = reinterpret_cast<const float2*>(cs);
+                const float2 u0 = __ldg(c2), u1 = __ldg(c2 + 1), u2 = __ldg(c2 + 2);
+                g.cs[0] = u0.x; g.cs[1] = u0.y; g.cs[2] = u1.x; g.cs[3] = u1.y; g.cs[4] = u2.x; g.cs[5] = u2.y;
+            } else {
+#pragma unroll
+                for (int i = 0; i < NS; ++i) g.cs[i] = cs[i];
+            }
+        }
         if (m >= 0) {
             g.q = a.tgt_spts[m];
             const Real* ct = a.tgt_cov + (size_t)m * NS;
@@ -433,14 +447,14 @@ __global__ void __launch_bounds__(OBJ_THREADS, 4) accumulate_kernel(const ObjArg
         return g;
     };
     int m_cur = load_match(0);
-    Gathered g_cur = gather(m_cur);
+    Gathered g_cur = gather(m_cur, 0);
     int m_next = load_match(1);
     for (int it = 0; it < a.ppt; ++it) {
         const int s = s_first + it * OBJ_THREADS;
         if (s >= end) break;
         const int bestpos = m_cur;
         const Gathered g = g_cur;
-        g_cur = gather(m_next);           // in flight during this iteration's arithmetic
+        g_cur = gather(m_next, it + 1);   // in flight during this iteration's arithmetic
         m_cur = m_next;
         m_next = load_match(it + 2);
         const size_t out_row = (size_t)ms.pt_begin + (size_t)(a.out_W ? a.src_perm[s] : 0);
@@ -450,7 +464,7 @@ __global__ void __launch_bounds__(OBJ_THREADS, 4) accumulate_kernel(const ObjArg
             }
             continue;
         }
-        const PRec<Real> p = a.src_spts[s];
+        const PRec<Real> p = g.p;
         double pp[3] = {0.0, 0.0, 0.0};  // p' = R p + t (gicp.py:119)
         {
             const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
@@ -474,16 +488,8 @@ __global__ void __launch_bounds__(OBJ_THREADS, 4) accumulate_kernel(const ObjArg
         }
         double Cs[NS], M[NS], W[NS], e[D], v[D];
         {
-            const Real* cs = a.src_cov + (size_t)s * NS;
-            if constexpr (sizeof(Real) == 4 && NS == 6) {
-                // 24-byte records, 8-byte aligned: three 64-bit loads instead of six 32-bit ones
-                const float2* c2 = reinterpret_cast<const float2*>(cs);
-                const float2 s0 = __ldg(c2), s1 = __ldg(c2 + 1), s2 = __ldg(c2 + 2);
-                Cs[0] = s0.x; Cs[1] = s0.y; Cs[2] = s1.x; Cs[3] = s1.y; Cs[4] = s2.x; Cs[5] = s2.y;
-            } else {
 #pragma unroll
-                for (int i = 0; i < NS; ++i) Cs[i] = (double)cs[i];
-            }
+            for (int i = 0; i < NS; ++i) Cs[i] = (double)g.cs[i];
 #pragma unroll
             for (int i = 0; i < NS; ++i) M[i] = (double)g.ct[i];
         }
