@@ -384,7 +384,10 @@ int launch_knn(gicpContext* h, CloudSet& cs, int* d_idx, double* d_dist, cudaStr
     return 0;
 }
 
-constexpr size_t OBJ_SMEM = 128 + (size_t)(OBJ_THREADS / 32) * OBJ_STAGE_BYTES;
+// per-warp TMA stages + the block's work list (one entry per point of the block)
+inline size_t obj_smem(int ppt) {
+    return 128 + (size_t)(OBJ_THREADS / 32) * OBJ_STAGE_BYTES + (size_t)OBJ_THREADS * ppt * sizeof(int);
+}
 
 // cell edges; never smaller than (search radius)/8 so that a lane's ball spans <= 17 cells per axis
 double auto_knn_cell(const gicpContext* h) {
@@ -508,10 +511,10 @@ int objective_args(gicpContext* h, ObjArgs<Real>& a, int& blocks_per_pair, bool 
         a.slice_end = (int)(S.n_total * (h->rank + 1) / h->n_ranks);
         span = a.slice_end - a.slice_begin;
     }
-    // enough blocks to fill the machine, as many points per thread as that allows (<= 16)
+    // enough blocks to fill the machine, as many points per thread as that allows (<= OBJ_MAX_PPT)
     const long long total_pts = (long long)std::max(span, 1) * S.n_clouds;
     int ppt = (int)(total_pts / (148LL * 8 * OBJ_THREADS));
-    ppt = std::max(1, std::min(16, ppt));
+    ppt = std::max(1, std::min(OBJ_MAX_PPT, ppt));
     a.ppt = ppt;
     blocks_per_pair = std::max(1, (span + OBJ_THREADS * ppt - 1) / (OBJ_THREADS * ppt));
     a.blocks_per_pair = blocks_per_pair;
@@ -578,6 +581,15 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
     sa.d_inliers = d_inliers;
     sa.n_active = h->n_active.as<int>();
     const dim3 ogrid(bpp, np);
+    // the search runs on smaller blocks than the accumulation (its work per point is uneven: better balance and
+    // a shorter tail), the accumulation keeps the longer per-thread pipeline
+    ObjArgs<Real> oc = oa;
+    {
+        int split = getenv("GICP_CORR_SPLIT") ? atoi(getenv("GICP_CORR_SPLIT")) : 2;
+        while (split > 1 && oa.ppt % split) --split;
+        oc.ppt = oa.ppt / std::max(split, 1);
+    }
+    const dim3 cgrid(bpp * (oa.ppt / oc.ppt), np);
     const int sgrid = (np + SOLVE_WARPS - 1) / SOLVE_WARPS;
     const bool sharded = h->comm && np == 1;
     *h->h_poll = np;
@@ -585,7 +597,7 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
     for (int it = 0; it < h->prm.max_iterations; ++it) {
         {
             ProfScope prof(h, GICP_STAGE_CORRESPOND, st);
-            correspond_kernel<D, Real><<<ogrid, OBJ_THREADS, OBJ_SMEM, st>>>(oa);
+            correspond_kernel<D, Real><<<cgrid, OBJ_THREADS, obj_smem(oc.ppt), st>>>(oc);
         }
         {
             ProfScope prof(h, GICP_STAGE_ACCUMULATE, st);
@@ -637,7 +649,7 @@ int do_stage(gicpContext* h, const double* h_T, int* d_idx, double* d_dist, doub
     oa.out_W = d_W;
     oa.ignore_status = 1;
     // stage entry points always cover the whole source (no slicing), so their outputs are complete
-    correspond_kernel<D, Real><<<dim3(bpp, np), OBJ_THREADS, OBJ_SMEM, st>>>(oa);
+    correspond_kernel<D, Real><<<dim3(bpp, np), OBJ_THREADS, obj_smem(oa.ppt), st>>>(oa);
     if (d_W || h_out) accumulate_kernel<D, Real><<<dim3(bpp, np), OBJ_THREADS, 0, st>>>(oa);
     h->launches += 2;
     if (h_out) {

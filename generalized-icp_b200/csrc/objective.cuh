@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
     //      Exact skip: at its last search the point's nearest neighbour was d1 away and every other
     //      target point at least d2 away.  While it has moved less than (d2 - d1) / 2 in total since
     //      then, the same target point is still strictly the nearest. ----
-    __shared__ int s_list[OBJ_THREADS * OBJ_MAX_PPT];
+    int* s_list = reinterpret_cast<int*>(smem_raw + 128 + (OBJ_THREADS / 32) * OBJ_STAGE_BYTES);   // [OBJ_THREADS * ppt]
     __shared__ int s_count;
     const int blk_begin = begin + blockIdx.x * a.ppt * OBJ_THREADS;
     const int blk_end = min(end, blk_begin + a.ppt * OBJ_THREADS);
