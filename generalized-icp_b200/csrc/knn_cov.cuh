@@ -159,25 +159,31 @@ __device__ __forceinline__ void knn_rank_and_finish(const KnnArgs<Real>& a, cons
         if ((float)lk[i * 32 + lane] < sure_thr) sel |= 1u << i;
         else amb |= 1u << i;
     }
-    // pass B: every lane ranks its next marked entry by counting, all lanes side by side
+    // pass B: every lane ranks its next marked entry by counting, all lanes side by side.  Only the marked
+    // entries are compared: every sure entry is closer than every marked one by more than the rounding of
+    // the fp32 keys, except within 5e-7 of the threshold itself, where both are below the k-th bin and the
+    // rank (at most n_sure + marked-below-the-bin - 1 <= k - 2) selects the entry either way.
+    const unsigned marked = amb;
+    if (n_sure >= a.k) n_sure = 0;
     while (amb) {
         const int i = __ffs(amb) - 1;
         amb &= amb - 1;
         const KeyT ki = lk[i * 32 + lane];
         const int ii = li[i * 32 + lane];
-        int r = 0;
+        int r = n_sure;
         if (sizeof(Real) == 4) {
             const float lo_k = (float)ki * 0.999999f, hi_k = (float)ki * 1.000001f;
             int below = 0, upto = 0;
-            for (int j = 0; j < mcount; ++j) {
-                const float kj = (float)lk[j * 32 + lane];
+            for (unsigned mm = marked; mm; mm &= mm - 1) {
+                const float kj = (float)lk[(__ffs(mm) - 1) * 32 + lane];
                 below += (kj < lo_k) ? 1 : 0;
                 upto += (kj <= hi_k) ? 1 : 0;
             }
-            r = below;
+            r += below;
             if (upto - below > 1) {   // another candidate inside the fp32 rounding band: exact keys decide
                 const double ei = exact_key(ii);
-                for (int j = 0; j < mcount; ++j) {
+                for (unsigned mm = marked; mm; mm &= mm - 1) {
+                    const int j = __ffs(mm) - 1;
                     const float kj = (float)lk[j * 32 + lane];
                     if (j != i && kj >= lo_k && kj <= hi_k) {
                         const int ij = li[j * 32 + lane];
@@ -186,7 +192,10 @@ __device__ __forceinline__ void knn_rank_and_finish(const KnnArgs<Real>& a, cons
                 }
             }
         } else {
-            for (int j = 0; j < mcount; ++j) r += key_less((double)lk[j * 32 + lane], li[j * 32 + lane], (double)ki, ii) ? 1 : 0;
+            for (unsigned mm = marked; mm; mm &= mm - 1) {
+                const int j = __ffs(mm) - 1;
+                r += key_less((double)lk[j * 32 + lane], li[j * 32 + lane], (double)ki, ii) ? 1 : 0;
+            }
         }
         if (r < a.k) {
             sel |= 1u << i;
