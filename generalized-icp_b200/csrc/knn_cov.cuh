@@ -14,9 +14,11 @@
 //      search stops once the searched box covers that bound for every lane;
 //   2. the box is streamed once more and each lane keeps the candidates under its bound (k plus
 //      the few that share the last bin) in a lane-private list;
-//   3. the list is ranked by counting.  The ranked key is the float64 squared distance
-//      (dx*dx + dy*dy) + dz*dz of the oracle, ties to the lower point index: fp32 keys decide every
-//      comparison that falls outside their rounding band, exact keys the rest.
+//   3. everything below the bin of the k-th candidate is in the set; the entries of that bin are marked and
+//      then ranked among themselves by counting, all lanes side by side.  The ranked key is the float64
+//      squared distance (dx*dx + dy*dy) + dz*dz of the oracle, ties to the lower point index: fp32 keys
+//      decide every comparison that falls outside their rounding band, exact keys the rest.  The moments of
+//      the selected neighbours are accumulated in a loop of their own (next gather in flight).
 // General path (knn_general_kernel): exact sorted top-k in registers fed through a per-lane queue;
 // used when k is too large for the fast path's list and for the warps whose list overflowed.
 #pragma once
