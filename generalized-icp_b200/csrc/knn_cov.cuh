@@ -382,7 +382,10 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Rea
         // ---- sweep 2: keep the candidates under the bound ----
         const int none[3] = {0, 0, 0};
         int cnt_l = 0;
-        const float lim2 = mine ? bound32 : -1.0f;
+        // The list takes every candidate up to the bound widened by the rounding of the fp32 keys: a candidate
+        // that is left out is then farther - in exact arithmetic - than the k candidates known to lie under the bound.
+        const float list32 = bound32 * 1.000002f;
+        const float lim2 = mine ? list32 : -1.0f;
         stream_cells<Real>(m, a.cell_start, a.lut, a.spts, lo, hi, none, none, false, ws, lane,
                            [&](const PRec<Real>* w, int n) {
             auto key_of = [&](const PRec<Real>& c) -> KeyT {
@@ -407,7 +410,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Rea
             }
         }, [&](int x0, int y0, int z0, int x1, int y1, int z1) {
             // only blocks that reach into some lane's ball are staged
-            return mine && cell_box_dist2(m, pad, (float)mx, (float)my, (float)mz, x0, y0, z0, x1, y1, z1) <= bound32;
+            return mine && cell_box_dist2(m, pad, (float)mx, (float)my, (float)mz, x0, y0, z0, x1, y1, z1) <= list32;
         });
         // ---- sweep 3 for this group's lanes (the list memory is recycled by the next group) ----
         const bool ovf = mine && cnt_l > CAP;
@@ -558,6 +561,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_lane_kernel(const KnnArgs<Rea
     // ---- sweep 2: keep the candidates under the bound (cells that reach into the ball only) ----
     __syncwarp();   // every lane is done with its histogram column before the list overwrites the memory
     int cnt_l = 0;
+    const float list32 = bound32 * 1.000002f;   // see knn_hist_kernel
     {
         const int z0 = (D == 3) ? max(cz - rho_fin, 0) : 0, z1 = (D == 3) ? min(cz + rho_fin, m.dims[2] - 1) : 0;
         const int y0 = max(cy - rho_fin, 0), y1 = min(cy + rho_fin, m.dims[1] - 1);
@@ -565,7 +569,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_lane_kernel(const KnnArgs<Rea
         for (int z = z0; z <= z1; ++z)
             for (int y = y0; y <= y1; ++y)
                 for (int x = x0; x <= x1; ++x) {
-                    if (cell_box_dist2(m, pad, (float)mx, (float)my, (float)mz, x, y, z, x, y, z) > bound32) continue;
+                    if (cell_box_dist2(m, pad, (float)mx, (float)my, (float)mz, x, y, z, x, y, z) > list32) continue;
                     const int* cs = CS + (__ldg(L + x) | __ldg(L + GICP_LUT_N + y) | __ldg(L + 2 * GICP_LUT_N + z));
                     const int j0 = __ldg(cs), j1 = __ldg(cs + 1);
                     for (int j = j0; j < j1; ++j) {
@@ -574,7 +578,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_lane_kernel(const KnnArgs<Rea
                         if (sizeof(Real) == 4) key = (KeyT)dist32(c);
                         else key = (KeyT)exact_d2((double)c.x - (double)mx, (double)c.y - (double)my,
                                                   (double)c.z - (double)mz);
-                        if ((float)key <= bound32) {
+                        if ((float)key <= list32) {
                             if (cnt_l < CAP) { lk[cnt_l * 32 + lane] = key; li[cnt_l * 32 + lane] = (int)c.idx; }
                             ++cnt_l;
                         }
