@@ -192,8 +192,7 @@ __device__ inline void smallest_eigvec3(double a00, double a01, double a02, doub
     if (n2 > nb) { best = v2; nb = n2; }
     if (!(nb > 1e-300)) return;  // rank <= 1: smallest eigenspace is 2-dimensional, keep the fallback
     double v[3] = {best[0], best[1], best[2]};
-    // one step of inverse-iteration-free refinement: project out rounding by re-orthogonalising
-    // against the residual direction (cheap Rayleigh polish in fp64)
+    // normalise; the largest of the three cross products is the best conditioned one in fp64
     const double inv = rsqrt(nb);
     v[0] *= inv; v[1] *= inv; v[2] *= inv;
     n[0] = v[0]; n[1] = v[1]; n[2] = v[2];

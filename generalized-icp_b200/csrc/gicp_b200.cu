@@ -130,6 +130,7 @@ struct gicpContext {
     DevBuf keys, keys_alt, vals, vals_alt, cub_tmp, cell_count, bbox_part;
     DevBuf state, partial, red, T_dev, n_active, prev_match, slack, ovf_count, ovf_list;
     int* h_poll = nullptr;  // pinned
+    cudaStream_t last_stream = nullptr;   // stream of the last gicpSet*/gicpRegister call (gicpPromoteTargetToSource has none)
     int64_t launches = 0;
     // per-stage CUDA-event timing (off by default): stage ids in include/gicp_b200.h
     bool prof_on = false;
@@ -406,6 +407,7 @@ int set_cloud(gicpContext* h, int which, const void* d_points, const int64_t* h_
               cudaStream_t st) {
     CloudSet& cs = which == GICP_TARGET ? h->tgt : h->src;
     cs.ready = false;
+    h->last_stream = st;
     if (n_clouds <= 0) return fail("n_clouds must be positive");
     if (n_clouds > 65535) return fail("at most 65535 clouds per batch (got %d)", n_clouds);
     cs.raw = d_points;
@@ -473,6 +475,19 @@ int set_cloud(gicpContext* h, int which, const void* d_points, const int64_t* h_
     }
     CU(cudaGetLastError());
     cs.ready = true;
+    return 0;
+}
+
+// gicpPromoteTargetToSource with an ICP-family model: the promoted side keeps its grids, but its covariances
+// were the TARGET's (I for point-to-point, the estimated ones for point-to-plane); a source has C = 0 in both.
+template <int D, typename Real>
+int zero_source_cov(gicpContext* h, cudaStream_t st) {
+    CloudSet& cs = h->src;
+    const size_t n = (size_t)std::max<int64_t>(cs.n_total, 1);
+    fill_cov_kernel<D, Real><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cs.cov_knn.as<Real>(), n, Real(0));
+    fill_cov_kernel<D, Real><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cs.cov_nn.as<Real>(), n, Real(0));
+    h->launches += 2;
+    CU(cudaGetLastError());
     return 0;
 }
 
@@ -556,6 +571,7 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
     int bpp = 1;
     if (objective_args<D, Real>(h, oa, bpp, true)) return 1;
     const int np = h->src.n_clouds;
+    h->last_stream = st;
     if (ensure_state<D, Real>(h, h_T0, d_T, d_T_hist, d_n_outer, d_converged, st)) return 1;
     CU(cudaMemcpyAsync(h->n_active.p, &np, sizeof(int), cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));
@@ -754,7 +770,8 @@ int gicpCreate(gicpHandle* out, int device, int dim, int storage) {
     CU(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 9) return fail("device %d is sm_%d%d; this library is built for sm_100a", device, prop.major, prop.minor);
+    if (prop.major != 10)
+        return fail("device %d is sm_%d%d; this library holds sm_100a code only (B200)", device, prop.major, prop.minor);
     gicpContext* h = new gicpContext();
     h->device = device;
     h->dim = dim;
@@ -812,6 +829,7 @@ int gicpPromoteTargetToSource(gicpHandle h) {
     if (!h->tgt.ready) return fail("no target to promote");
     std::swap(h->src, h->tgt);   // both sides own the same kind of state (two grids + covariances)
     h->tgt.ready = false;
+    if (h->prm.covariance_model != GICP_PLANE_TO_PLANE) return DISPATCH(h, zero_source_cov, h, h->last_stream);
     return 0;
 }
 
@@ -869,6 +887,7 @@ int gicpCommInit(gicpHandle h, int32_t n_ranks, int32_t rank, const char id[128]
     void* comm = nullptr;
     int rc = g_nccl.CommInitRank(&comm, n_ranks, u, rank);
     if (rc) return fail("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     h->comm = comm;
     h->n_ranks = n_ranks;
     h->rank = rank;

@@ -397,6 +397,12 @@ __global__ void __launch_bounds__(OBJ_THREADS, 4) accumulate_kernel(const ObjArg
     if (a.slice_begin >= 0) { begin = max(begin, a.slice_begin); end = min(end, a.slice_end); }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (begin >= end) {
+        // empty source cloud (or empty shard slice): nothing to gather - the pipeline below would read the record
+        // before `begin`.  The pair's partial rows are zero.
+        if (threadIdx.x < NRED) a.partial[((size_t)pair * a.blocks_per_pair + blockIdx.x) * NRED + threadIdx.x] = 0.0;
+        return;
+    }
     AccT acc[NQ];
 #pragma unroll
     for (int i = 0; i < NQ; ++i) acc[i] = AccT(0);

@@ -286,6 +286,43 @@ def reduced_form_loss(red, dim, T_lin, T_eval):
     return float(c - 2.0 * np.sum(G * Z) + quad)
 
 
+def reduced_form_grad2d(red, T_lin, x):
+    """Gradient of the frozen inner objective with respect to the reference's parameters (tx, ty, theta)
+    (what grad_loss returns, gicp.py:60-76), derived from the reduced form K3 accumulates:
+    f(Z) = c - 2<G,Z> + <Z,HZ>, Z(x) = [dt_c | dR - I], dR = R(theta) R_lin^-1, dt_c = t - dR t_lin + (dR - I) mu,
+    so df/dx = <2 (H Z - G), dZ/dx>."""
+    d, NP, NS = 2, 3, 3
+    NAB = NP * (NP + 1) // 2
+    NH = NAB * NS
+    Hq = red[:NH].reshape(NAB, NS)
+    G = red[NH:NH + d * NP].reshape(d, NP)
+    mu = red[NH + d * NP + 2:NH + d * NP + 2 + d]
+    th = float(x[2])
+    R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    dRdth = np.array([[-np.sin(th), -np.cos(th)], [np.cos(th), -np.sin(th)]])
+    Rl_inv = np.linalg.inv(T_lin[:d, :d])
+    dR = R @ Rl_inv
+    dtc = np.asarray(x[:2], dtype=np.float64) - dR @ T_lin[:d, d] + (dR - np.eye(d)) @ mu
+    Z = np.concatenate([dtc[:, None], dR - np.eye(d)], axis=1)
+
+    def sym(n, a, b):
+        a, b = min(a, b), max(a, b)
+        return a * n - a * (a - 1) // 2 + (b - a)
+
+    HZ = np.zeros_like(Z)
+    for cc in range(d):
+        for a in range(NP):
+            HZ[cc, a] = sum(Hq[sym(NP, a, b), sym(d, cc, dd)] * Z[dd, b] for dd in range(d) for b in range(NP))
+    Gam = 2.0 * (HZ - G)
+    grad = np.zeros(3)
+    for c in range(d):                                   # d/dt_c: dZ = e_c in column 0
+        grad[c] = Gam[c, 0]
+    dRp = dRdth @ Rl_inv                                 # d/dtheta
+    dZ = np.concatenate([(-dRp @ T_lin[:d, d] + dRp @ mu)[:, None], dRp], axis=1)
+    grad[2] = float(np.sum(Gam * dZ))
+    return grad
+
+
 def ray_cast(poses, num_rays=90, obstacles=None, max_range=400.0, noise=None, device=None):
     """Batched LiDAR scans on the device (robot-visualization.py:42-120, 222-237).
     poses: (n, 3) x, y, yaw_deg.  obstacles: list of (x, y, w, h) rectangles and (cx, cy, r) circles - default

@@ -18,7 +18,9 @@
  *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it
  *    unless they return host data (those synchronise the stream).
  *  - a handle is bound to one device and one (dim, storage) pair and is not
- *    thread-safe: one handle per thread/stream.
+ *    thread-safe: one handle per thread.  All calls on a handle must use the SAME
+ *    stream (the source and target sides share the handle's scratch buffers;
+ *    two streams would race on them).
  *  - clouds come as BATCHES: `n_clouds` clouds concatenated into one (n_total,
  *    dim) row-major array, with h_offsets[n_clouds+1] giving each cloud's row
  *    range.  A single pair is a batch of one.  Source cloud i is registered
@@ -54,7 +56,8 @@ typedef struct gicpParams {
     int32_t covariance_model;     /* ICP family through the same kernels (presentation/main.typ:446-462):
                                    * 0 plane-to-plane = GICP (the reference), 1 point-to-point (C_A = 0, C_B = I),
                                    * 2 point-to-plane (C_A = 0, C_B = the target's surface-aligned covariance)    */
-    double  knn_cell;             /* uniform-grid cell edge for the k-NN grid; 0 = auto (radius / 2)      */
+    double  knn_cell;             /* uniform-grid cell edge for the k-NN grid; 0 = auto (radius / 4);   */
+                                  /* a given value is raised to at least radius / 8                       */
     double  nn_cell;              /* cell edge of the target's 1-NN grid;      0 = auto (d_max / 2)       */
     int64_t max_cells_per_cloud;  /* cell-table budget per cloud; 0 = auto                                */
 } gicpParams;

@@ -13,6 +13,8 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 from generalized_icp_b200 import compat, synthetic  # noqa: E402
 from generalized_icp_b200.engine import GicpEngine  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import demo_inputs  # noqa: E402  (seeded restatements of the demos' input recipes)
 
 rank = int(os.environ.get("RANK", "0"))
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -34,7 +36,7 @@ def timed(fn, reps):
 if "1" in which and rank == 0:
     ts, its = [], []
     for seed in range(8):
-        s, t = synthetic.config1_pair(seed)
+        s, t = demo_inputs.config1_pair(seed)
         dt, r = timed(lambda: compat.gicp_extended(s, t, full_history=False), 5)
         ts.append(dt)
         its.append(r["n_outer"])
@@ -43,7 +45,7 @@ if "1" in which and rank == 0:
 
 if "2" in which and rank == 0:
     for rays in (90, 360):
-        scans, _ = synthetic.lidar_sequence(seed=1, num_rays=rays, n_scans=30)
+        scans, _ = demo_inputs.lidar_sequence(seed=1, num_rays=rays, n_scans=30)
         pairs = [(np.asarray(scans[i]), np.asarray(scans[i + 1])) for i in range(len(scans) - 1)]
 
         def run():

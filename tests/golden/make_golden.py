@@ -31,8 +31,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, "/root/reference/python-implementation")
 import gicp as ref  # noqa: E402  (the reference module)
 
-sys.path.insert(0, os.path.join(ROOT, "generalized-icp_b200"))
-import synthetic  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import demo_inputs  # noqa: E402
 
 
 def cells(fn):
@@ -94,10 +94,10 @@ def run_case(src, tgt, **kw):
 def main():
     made = []
     for seed in range(6):
-        s, t = synthetic.config1_pair(seed)
+        s, t = demo_inputs.config1_pair(seed)
         made.append((f"config1_seed{seed}", run_case(s, t)))
     for rays, n_scans in ((90, 11), (360, 7)):
-        scans, _ = synthetic.lidar_sequence(seed=1, num_rays=rays, n_scans=n_scans)
+        scans, _ = demo_inputs.lidar_sequence(seed=1, num_rays=rays, n_scans=n_scans)
         for i in range(len(scans) - 1):
             # source = previous scan, target = current (robot-visualization.py:250-251)
             made.append((f"config2_rays{rays}_pair{i}",

@@ -59,10 +59,10 @@ def test_covariances(name, golden, torch_cuda):
 
 @pytest.mark.parametrize("name", SMALL)
 def test_correspondences_weights_loss_teacher_forced(name, golden, torch_cuda):
-    """Feed the reference's own T_k: 1-NN indices bit-exact (gicp.py:132-138), W (gicp.py:145) and the
-    value of the frozen inner objective at the reference's x0 / xopt (gicp.py:52-58) from the
-    reduced form K3 accumulates."""
-    from generalized_icp_b200.engine import reduced_form_loss
+    """Feed the reference's own T_k: 1-NN indices bit-exact (gicp.py:132-138), W (gicp.py:145), and the
+    value (gicp.py:52-58) and gradient (gicp.py:60-76) of the frozen inner objective at the reference's
+    x0 / xopt, both from the reduced form K3 accumulates."""
+    from generalized_icp_b200.engine import reduced_form_grad2d, reduced_form_loss
     g = golden(name)
     eng = _engine2d(g, torch_cuda)
     for k in range(len(g["it_fopt"])):
@@ -83,6 +83,10 @@ def test_correspondences_weights_loss_teacher_forced(name, golden, torch_cuda):
             want = float(g[lk][k])
             got = reduced_form_loss(red, 2, T, Te)
             assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), (k, xk, got, want)
+            # grad_loss (gicp.py:60-76) at the same point, from the same 32 doubles
+            gw = g[lk.replace("loss", "grad")][k]
+            gg = reduced_form_grad2d(red, T, x)
+            assert np.abs(gg - gw).max() <= 1e-7 * max(1.0, np.abs(gw).max()), (k, xk, gg, gw)
 
 
 def _compat(g, **kw):
@@ -92,23 +96,94 @@ def _compat(g, **kw):
                                 max_distance_nearest_neighbors=float(g["r_knn"]), **kw)
 
 
-@pytest.mark.parametrize("name", [n for n in SMALL if n.startswith("config2")])
-def test_end_to_end_vs_reference_config2(name, golden, torch_cuda):
-    """Well-conditioned consecutive scans: where every fmin_cg call of the reference converged
-    (warnflag 0) the iteration count is identical and T agrees to 1e-4 rad / 1e-2 px (fmin_cg's own
-    gtol=1e-5 exit leaves it that far from the minimiser)."""
+# Where the engine's end-to-end result is known to leave the reference's: a converged inner solve (the engine, and
+# the oracle with inner="newton") against fmin_cg stopping unconverged (warnflag 1/2 on about half of config 1's
+# outer iterations).  Established on the CPU with the oracle (tests/golden/make_match_rate.py prints the
+# same for seeds 0-39) and asserted here BOTH ways, so neither a regression nor a silent improvement goes unnoticed.
+# value: (iteration count of the converged solve, "count" | "T" = what differs from the reference)
+KNOWN_DEVIATIONS = {
+    "config1_seed0": (16, "count"),          # reference 14; ends 0.155 px / 6e-4 rad away
+    "config1_seed2": (23, "count"),          # reference 17
+    "config1_seed5": (18, "count"),          # reference 17
+    "config2_rays360_pair0": (4, "T"),       # same count; the reference's CG stops 1.4e-3 rad / 0.42 px short
+    "config2_rays360_pair4": (5, "count"),   # reference 4
+}
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_end_to_end_vs_reference(name, golden, torch_cuda):
+    """Final transform and iteration count against the UNMODIFIED reference's own run (gicp.py:78-174), every
+    fixture: identical iteration count and T within 1e-4 rad / 1e-2 px (fmin_cg's own gtol = 1e-5 exit leaves it
+    that far from the minimiser), except the fixtures of KNOWN_DEVIATIONS, which must deviate exactly as recorded."""
     g = golden(name)
     r = _compat(g)
-    if (g["it_warnflag"] == 0).all():
-        assert r["n_outer"] == len(g["it_fopt"])
+    n_ref = len(g["it_fopt"])
+    d_ang = abs(np.arctan2(r["T"][1, 0], r["T"][0, 0]) - np.arctan2(g["T"][1, 0], g["T"][0, 0]))
+    d_t = np.abs(r["T"][:2, 2] - g["T"][:2, 2]).max()
+    if name in KNOWN_DEVIATIONS:
+        n_conv, what = KNOWN_DEVIATIONS[name]
+        assert r["n_outer"] == n_conv
+        if what == "count":
+            assert n_conv != n_ref
+        else:
+            assert n_conv == n_ref and (d_ang >= 1e-4 or d_t >= 1e-2)
+    else:
+        assert r["n_outer"] == n_ref
         assert len(r["all_T"]) == len(g["all_T"])
         assert len(r["all_src_cov"]) == len(g["all_src_cov"])
         assert len(r["hw_src"]) == int(g["n_hw"])
-        d_ang = abs(np.arctan2(r["T"][1, 0], r["T"][0, 0]) - np.arctan2(g["T"][1, 0], g["T"][0, 0]))
-        assert d_ang < 1e-4
-        assert np.abs(r["T"][:2, 2] - g["T"][:2, 2]).max() < 1e-2
-    else:
-        assert r["n_outer"] >= 1
+        assert d_ang < 1e-4 and d_t < 1e-2
+
+
+def test_match_rate_vs_reference(torch_cuda):
+    """The match rate over the BASELINE configs 1-2 against the unmodified reference (outcomes recorded by
+    tests/golden/make_match_rate.py): config 1 seeds 0-39, config 2 drives of 30 scans at 90 and 360 rays.
+    Reported to gpurun_out/parity_vs_reference.json (committed as profiles/parity_vs_reference_r02.md) and
+    asserted not to regress.  The engine must also agree with the converged-inner-solve oracle on every case."""
+    import json
+    import os
+    import demo_inputs
+    from conftest import GOLDEN, ROOT
+    from generalized_icp_b200 import compat
+    m = dict(np.load(os.path.join(GOLDEN, "match_rate_reference.npz")))
+    drives = {rays: demo_inputs.lidar_sequence(seed=1, num_rays=rays, n_scans=30)[0] for rays in (90, 360)}
+    rows = {}
+    for i in range(len(m["kind"])):
+        kind, seed, rays, pair = (int(m[k][i]) for k in ("kind", "seed", "rays", "pair"))
+        if kind == 1:
+            s, t = demo_inputs.config1_pair(seed)
+            kw, key = {}, "config1"
+        else:
+            s, t = np.asarray(drives[rays][pair]), np.asarray(drives[rays][pair + 1])
+            kw, key = dict(max_distance_nearest_neighbors=200, tolerance=1), f"config2_rays{rays}"
+        r = compat.gicp_extended(s, t, full_history=False, **kw)
+
+        def close(T, tol_ang, tol_t):
+            d_ang = abs(np.arctan2(r["T"][1, 0], r["T"][0, 0]) - np.arctan2(T[1, 0], T[0, 0]))
+            return bool(d_ang < tol_ang and np.abs(r["T"][:2, 2] - T[:2, 2]).max() < tol_t)
+
+        row = rows.setdefault(key, dict(cases=0, same_iterations_as_reference=0, T_close_to_reference=0,  # 1e-5 rad, 1e-2 px
+                                        reference_cg_always_converged=0, same_iterations_as_converged_oracle=0,
+                                        T_close_to_converged_oracle=0))   # max |dT| < 1e-6
+        row["cases"] += 1
+        row["same_iterations_as_reference"] += int(r["n_outer"] == int(m["n_ref"][i]))
+        row["T_close_to_reference"] += int(close(m["T_ref"][i], 1e-5, 1e-2))
+        row["reference_cg_always_converged"] += int(bool(m["clean"][i]))
+        row["same_iterations_as_converged_oracle"] += int(r["n_outer"] == int(m["n_newton"][i]))
+        row["T_close_to_converged_oracle"] += int(np.abs(r["T"] - m["T_newton"][i]).max() < 1e-6)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_vs_reference.json"), "w") as f:
+        json.dump(dict(rows=rows, versions=str(m["versions"])), f, indent=1)
+    # floors = what the converged-inner-solve oracle achieves on the CPU (22/40 and 34/40; 29/29 and 29/29; 28/29 and 26/29)
+    c1, c90, c360 = rows["config1"], rows["config2_rays90"], rows["config2_rays360"]
+    assert c1["same_iterations_as_reference"] >= 21 and c1["T_close_to_reference"] >= 33
+    assert c90["same_iterations_as_reference"] >= 29 and c90["T_close_to_reference"] >= 29
+    assert c360["same_iterations_as_reference"] >= 28 and c360["T_close_to_reference"] >= 26
+    # against the well-defined target every case must agree; config 1's chaotic trajectories (60 degrees off at the
+    # start) are allowed two count mismatches out of 40
+    assert c1["same_iterations_as_converged_oracle"] >= 38
+    assert c90["same_iterations_as_converged_oracle"] == 29 and c360["same_iterations_as_converged_oracle"] == 29
+    assert c90["T_close_to_converged_oracle"] == 29 and c360["T_close_to_converged_oracle"] >= 28
 
 
 @pytest.mark.parametrize("name", SMALL)
@@ -271,9 +346,10 @@ def test_scan_sequence_reuse_is_bit_identical(torch_cuda):
     """Promoting the target to the next pair's source gives bit-identical transforms to registering
     every pair from scratch through the drop-in gicp(), and the integrated pose follows the
     simulated robot (robot-visualization.py:258-265)."""
-    from generalized_icp_b200 import compat, synthetic
+    import demo_inputs
+    from generalized_icp_b200 import compat
     from generalized_icp_b200.odometry import ScanOdometry, integrate_pose, trajectory_errors
-    scans, truth = synthetic.lidar_sequence(seed=2, num_rays=360, n_scans=14)
+    scans, truth = demo_inputs.lidar_sequence(seed=2, num_rays=360, n_scans=14)
     odo = ScanOdometry(start_pose=(50.0, 400.0, 0.0))
     for s in scans:
         odo.push(s)
@@ -430,9 +506,9 @@ def test_icp_variants_vs_oracle(model, torch_cuda):
 def test_ray_caster_matches_demo(num_rays, torch_cuda):
     import math
     import random
-    from generalized_icp_b200 import synthetic
+    import demo_inputs
     from generalized_icp_b200.engine import ray_cast
-    sim = synthetic.LidarSim(seed=0, num_rays=num_rays)
+    sim = demo_inputs.LidarSim(seed=0, num_rays=num_rays)
     poses, want, noises = [], [], []
     for step in range(25):
         sim.step(up=True, right=(step % 7 == 3), left=(step % 11 == 5))
@@ -483,3 +559,51 @@ def test_register_host_batch_matches_device_batch(torch_cuda):
     assert np.array_equal(T_h.numpy(), r.T.cpu().numpy())
     assert np.array_equal(n_h.numpy(), r.n_outer.cpu().numpy())
     assert np.array_equal(c_h.numpy(), r.converged_at.cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------------
+# round-2 review items
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("model", [1, 2])
+def test_scan_sequence_reuse_with_icp_variants(model, torch_cuda):
+    """gicpPromoteTargetToSource with covariance_model 1 / 2: the promoted side held TARGET covariances
+    (I, or the estimated ones); as a source it must have C = 0 like a freshly set source."""
+    import demo_inputs
+    from generalized_icp_b200 import compat
+    from generalized_icp_b200.odometry import ScanOdometry
+    scans, _ = demo_inputs.lidar_sequence(seed=4, num_rays=360, n_scans=6)
+    odo = ScanOdometry(start_pose=(50.0, 400.0, 0.0), covariance_model=model)
+    for s in scans:
+        odo.push(s)
+    for i in range(len(scans) - 1):
+        r = compat.gicp_extended(np.asarray(scans[i]), np.asarray(scans[i + 1]), max_distance_nearest_neighbors=200,
+                                 tolerance=1, full_history=False, covariance_model=model)
+        assert np.array_equal(r["T"], odo.transforms[i]), i
+        assert r["n_outer"] == odo.iterations[i]
+
+
+def test_empty_clouds_inside_a_batch(torch_cuda):
+    """An empty source cloud FIRST in the batch (a LiDAR scan with zero hits), an empty target cloud, and a
+    regular pair after them: no out-of-bounds read, identity for the empty pairs, the regular pair unchanged."""
+    torch = torch_cuda
+    from generalized_icp_b200.engine import GicpEngine
+    sA, tA, _ = _pair3(0, n=1400)
+    sB, tB, _ = _pair3(1, n=1500)
+    eng = GicpEngine(3, "f32")
+    eng.set_params(**P3)
+    eng.set_target(torch.as_tensor(tB, device="cuda"))
+    eng.set_source(torch.as_tensor(sB, device="cuda"))
+    alone = eng.register()
+    S = torch.as_tensor(np.concatenate([sA, sB]), device="cuda")
+    T = torch.as_tensor(np.concatenate([tA, tB]), device="cuda")
+    eng.set_target(T, [0, len(tA), len(tA), len(tA) + len(tB)])          # pair 1: empty target
+    eng.set_source(S, [0, 0, len(sA), len(sA) + len(sB)])                # pair 0: empty source
+    r = eng.register()
+    torch.cuda.synchronize()
+    eye = np.eye(4)
+    assert np.array_equal(r.T[0].cpu().numpy(), eye) and np.array_equal(r.T[1].cpu().numpy(), eye)
+    assert int(r.converged_at[0]) == 1 and int(r.converged_at[1]) == 1   # loss 0 twice -> stop at iteration 1
+    assert np.array_equal(r.T[2].cpu().numpy(), alone.T[0].cpu().numpy())
+    assert int(r.n_outer[2]) == int(alone.n_outer[0])
+    idx, _, _ = eng.correspond(np.stack([eye, eye, eye]), with_W=False)
+    assert (idx[:len(sA)].cpu().numpy() == -1).all()                      # nothing to match in an empty target

@@ -66,14 +66,64 @@ def test_product_path_does_not_import_oracle():
 
 
 def test_generators_are_seeded(golden):
+    import demo_inputs
     from generalized_icp_b200 import synthetic
     g = golden("config1_seed0")
-    s, t = synthetic.config1_pair(0)
+    s, t = demo_inputs.config1_pair(0)
     assert np.array_equal(s, g["src"]) and np.array_equal(t, g["tgt"])
     assert s.shape == (90, 2) and t.shape == (87, 2)
-    scans, poses = synthetic.lidar_sequence(seed=1, num_rays=90, n_scans=3)
+    scans, poses = demo_inputs.lidar_sequence(seed=1, num_rays=90, n_scans=3)
     g2 = golden("config2_rays90_pair0")
     assert np.array_equal(np.asarray(scans[0]), g2["src"]) and np.array_equal(np.asarray(scans[1]), g2["tgt"])
     a, b, T = synthetic.patches3d_pair(n=1000, seed=5)
     a2, b2, T2 = synthetic.patches3d_pair(n=1000, seed=5)
     assert a.dtype == np.float32 and np.array_equal(a, a2) and np.array_equal(b, b2) and np.array_equal(T, T2)
+
+
+def _reduced_form_numpy(src, q, W, T_lin, mu):
+    """The reduced form K3 accumulates (layout: include/gicp_b200.h), evaluated in numpy from the
+    reference's own matches q and weights W (rows with W = 0 are gated out)."""
+    d = 2
+    NP, NS = 3, 3
+    pp = src @ T_lin[:d, :d].T + T_lin[:d, d]
+    e = q - pp
+    pt = np.concatenate([np.ones((len(src), 1)), pp - mu], axis=1)
+    red = np.zeros(32)
+    ab = 0
+    for a in range(NP):
+        for b in range(a, NP):
+            for cd, (c, dd) in enumerate(((0, 0), (0, 1), (1, 1))):
+                red[ab * NS + cd] = np.sum(pt[:, a] * pt[:, b] * W[:, c, dd])
+            ab += 1
+    We = np.einsum("nij,nj->ni", W, e)
+    NH = 18
+    for c in range(d):
+        for a in range(NP):
+            red[NH + c * NP + a] = np.sum(We[:, c] * pt[:, a])
+    red[NH + d * NP] = np.sum(e * We)
+    red[NH + d * NP + 1] = np.count_nonzero(np.abs(W).sum((1, 2)))
+    red[NH + d * NP + 2:NH + d * NP + 4] = mu
+    return red
+
+
+@pytest.mark.parametrize("name", ["config1_seed0", "config1_seed3", "config2_rays90_pair0", "config2_rays360_pair2"])
+def test_reduced_form_reproduces_loss_and_grad_loss(name, golden):
+    """gicp.py:52-76: the value AND the gradient (tx, ty, theta) of the frozen inner objective follow from the
+    32-double reduced form; checked here against what the reference's own loss / grad_loss returned at x0 and
+    xopt of every outer iteration (the same helpers are applied to the GPU's reduced form in test_gpu_parity)."""
+    from generalized_icp_b200.engine import reduced_form_grad2d, reduced_form_loss
+    g = golden(name)
+    mu = 0.5 * (g["tgt"].min(0) + g["tgt"].max(0))
+    for k in range(len(g["it_fopt"])):
+        T = g["all_T"][k]
+        red = _reduced_form_numpy(g["src"], g["it_q"][k], g["it_W"][k], T, mu)
+        for xk, lk, gk in (("it_x0", "it_loss_at_x0", "it_grad_at_x0"), ("it_xopt", "it_loss_at_xopt", "it_grad_at_xopt")):
+            x = g[xk][k]
+            Te = np.eye(3)
+            Te[:2, :2] = [[np.cos(x[2]), -np.sin(x[2])], [np.sin(x[2]), np.cos(x[2])]]
+            Te[:2, 2] = x[:2]
+            want = float(g[lk][k])
+            assert abs(reduced_form_loss(red, 2, T, Te) - want) <= 1e-9 * max(1.0, abs(want))
+            gw = g[gk][k]
+            gg = reduced_form_grad2d(red, T, x)
+            assert np.abs(gg - gw).max() <= 1e-8 * max(1.0, np.abs(gw).max()), (k, xk, gg, gw)
