@@ -13,7 +13,8 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
 
 
-def golden_names(prefix=""):
+def golden_names(prefix="config"):
+    """Per-case fixtures recorded by tests/golden/make_golden.py (match_rate_reference.npz is a summary file)."""
     return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f.startswith(prefix))
 
 
