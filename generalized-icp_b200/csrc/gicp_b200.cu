@@ -393,6 +393,7 @@ inline size_t obj_smem(int ppt) {
 // cell edges; never smaller than (search radius)/8 so that a lane's ball spans <= 17 cells per axis
 double auto_knn_cell(const gicpContext* h) {
     const double r = h->prm.max_distance_nearest_neighbors;
+    if (getenv("GICP_KNN_CELL") && atof(getenv("GICP_KNN_CELL")) > 0) return std::max(atof(getenv("GICP_KNN_CELL")), r / 8.0);   // A/B timing
     if (h->prm.knn_cell > 0) return std::max(h->prm.knn_cell, r / 8.0);
     return 0.25 * r;   // measured optimum of the cooperative fast path on the bench workload (r = 5 m -> 1.25 m cells)
 }
