@@ -63,12 +63,12 @@ struct DevBuf {
 };
 
 struct Grid {
-    DevBuf meta, cell_start, spts, inv_perm, perm, bbox, lut;
+    DevBuf meta, cell_start, spts, inv_perm, bbox, lut;
     long long budget = 0;
     long long total_cells = 0;
     double h_target = 0;
     bool built = false;
-    void release() { meta.release(); cell_start.release(); spts.release(); inv_perm.release(); perm.release(); bbox.release(); lut.release(); }
+    void release() { meta.release(); cell_start.release(); spts.release(); inv_perm.release(); bbox.release(); lut.release(); }
 };
 
 struct CloudSet {
@@ -78,12 +78,16 @@ struct CloudSet {
     int64_t n_total = 0;
     int max_n = 0;
     DevBuf d_offsets;   // int32 [n_clouds+1]
-    Grid knn;           // grid of the covariance neighbourhoods (cell ~ knn radius / 2)
+    Grid knn;           // grid of the covariance neighbourhoods (cell ~ knn radius / 4)
     Grid nn;            // grid of the correspondence search (cell ~ d_max / 2): the target is searched in it,
-                        // the source is only ORDERED by it (compact warps in K3)
+                        // the source is only ORDERED by it (compact warps in K3).  Built only when the k-NN
+                        // grid's cells do not suit the search (`shared` = false)
     DevBuf cov_knn;     // covariances in knn-grid order (written by K2)
-    DevBuf cov_nn;      // the same covariances in nn-grid order (read by K3)
+    DevBuf cov_nn;      // the same covariances in nn-grid order (read by K3); unused when shared
+    bool shared = true; // one grid serves both stages: half the grid builds, no covariance re-ordering
     bool ready = false;
+    Grid& nng() { return shared ? knn : nn; }
+    DevBuf& covnn() { return shared ? cov_knn : cov_nn; }
     void release() { d_offsets.release(); knn.release(); nn.release(); cov_knn.release(); cov_nn.release(); }
 };
 
@@ -172,8 +176,7 @@ struct ProfScope {
 };
 
 template <int D, typename Real>
-int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, bool want_inv_perm, bool idx_is_pos,
-               cudaStream_t st) {
+int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, cudaStream_t st) {
     const int nc = cs.n_clouds;
     const int64_t n = cs.n_total;
     long long budget = h->prm.max_cells_per_cloud;
@@ -195,8 +198,7 @@ int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, bool want
     CU(g.cell_start.ensure((size_t)(g.total_cells + 1) * sizeof(int)));
     CU(h->cell_count.ensure((size_t)(g.total_cells + 1) * sizeof(int)));
     CU(g.spts.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(PRec<Real>)));
-    if (want_inv_perm) CU(g.inv_perm.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(int)));
-    if (idx_is_pos) CU(g.perm.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(int)));
+    CU(g.inv_perm.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(int)));
     CU(h->keys.ensure((size_t)std::max<int64_t>(n, 1) * 4));
     CU(h->keys_alt.ensure((size_t)std::max<int64_t>(n, 1) * 4));
     CU(h->vals.ensure((size_t)std::max<int64_t>(n, 1) * 4));
@@ -239,9 +241,7 @@ int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, bool want
         h->launches += (bits + 7) / 8 + 2;
         const int bx = (cs.max_n + 255) / 256;
         gather_sorted_kernel<D, Real><<<dim3(bx, nc), 256, 0, st>>>(pts, g.meta.as<CloudMeta>(), dv.Current(),
-                                                                    g.spts.as<PRec<Real>>(),
-                                                                    want_inv_perm ? g.inv_perm.as<int>() : nullptr,
-                                                                    idx_is_pos ? g.perm.as<int>() : nullptr);
+                                                                    g.spts.as<PRec<Real>>(), g.inv_perm.as<int>());
         h->launches += 1;
     }
     CU(cudaGetLastError());
@@ -250,14 +250,14 @@ int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, bool want
 }
 
 template <int D, typename Real>
-__global__ void regather_cov_kernel(const CloudMeta* __restrict__ meta, const int* __restrict__ perm_dst,
+__global__ void regather_cov_kernel(const CloudMeta* __restrict__ meta, const PRec<Real>* __restrict__ spts_dst,
                                     const int* __restrict__ inv_perm_src, const Real* __restrict__ cov_src,
                                     Real* __restrict__ cov_dst) {
     constexpr int NS = Dim<D>::NS;
     const CloudMeta m = meta[blockIdx.y];
     const int s = m.pt_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= m.pt_end) return;
-    const int g = m.pt_begin + perm_dst[s];
+    const int g = m.pt_begin + (int)spts_dst[s].idx;
     const int ss = inv_perm_src[g];
 #pragma unroll
     for (int i = 0; i < NS; ++i) cov_dst[(size_t)s * NS + i] = cov_src[(size_t)ss * NS + i];
@@ -399,6 +399,7 @@ double auto_knn_cell(const gicpContext* h) {
 }
 double auto_nn_cell(const gicpContext* h) {
     const double r = h->prm.max_distance_correspondence;
+    if (getenv("GICP_NN_CELL") && atof(getenv("GICP_NN_CELL")) > 0) return std::max(atof(getenv("GICP_NN_CELL")), r / 8.0);   // A/B timing
     if (h->prm.nn_cell > 0) return std::max(h->prm.nn_cell, r / 8.0);
     return 0.5 * r;
 }
@@ -431,7 +432,12 @@ int set_cloud(gicpContext* h, int which, const void* d_points, const int64_t* h_
 
     const double h_knn = auto_knn_cell(h);
     const double h_nn = auto_nn_cell(h);
-    if (build_grid<D, Real>(h, cs, cs.knn, h_knn, true, false, st)) return 1;
+    // one grid for both stages when the k-NN cell suits the correspondence search: not larger than twice the search's
+    // own choice (d_max / 2) and not smaller than d_max / 8 (a lane's ball then spans <= 17 cells per axis).  Measured
+    // on the bench workload (k-NN cell 1.25 m, search cell 1.0 m): K3a 14.97 vs 15.16 ms per 512 pairs - no loss.
+    cs.shared = h_knn <= 2.0 * h_nn && h_knn >= h->prm.max_distance_correspondence / 8.0 &&
+                !(getenv("GICP_SHARED_GRID") && atoi(getenv("GICP_SHARED_GRID")) == 0);
+    if (build_grid<D, Real>(h, cs, cs.knn, h_knn, st)) return 1;
     CU(cs.cov_knn.ensure((size_t)std::max<int64_t>(cs.n_total, 1) * ns_of(D) * sizeof(Real)));
 
     // covariances; in sharded mode every rank computes an equal slice (k-NN grid order) of BOTH clouds
@@ -463,13 +469,13 @@ int set_cloud(gicpContext* h, int which, const void* d_points, const int64_t* h_
         int rc = g_nccl.AllGather(basep + bytes * h->rank, basep, bytes, NCCL_INT8, h->comm, st);
         if (rc) return fail("ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
     }
-    {   // second ordering for the correspondence stage + the covariances carried over to it
-        if (build_grid<D, Real>(h, cs, cs.nn, h_nn, false, true, st)) return 1;
+    if (!cs.shared) {   // second ordering for the correspondence stage + the covariances carried over to it
+        if (build_grid<D, Real>(h, cs, cs.nn, h_nn, st)) return 1;
         CU(cs.cov_nn.ensure((size_t)std::max<int64_t>(cs.n_total, 1) * ns_of(D) * sizeof(Real)));
         if (cs.n_total > 0) {
             const int bx = (cs.max_n + 255) / 256;
             regather_cov_kernel<D, Real><<<dim3(bx, n_clouds), 256, 0, st>>>(
-                cs.nn.meta.as<CloudMeta>(), cs.nn.perm.as<int>(), cs.knn.inv_perm.as<int>(), cs.cov_knn.as<Real>(),
+                cs.nn.meta.as<CloudMeta>(), cs.nn.spts.as<PRec<Real>>(), cs.knn.inv_perm.as<int>(), cs.cov_knn.as<Real>(),
                 cs.cov_nn.as<Real>());
             h->launches += 1;
         }
@@ -486,8 +492,8 @@ int zero_source_cov(gicpContext* h, cudaStream_t st) {
     CloudSet& cs = h->src;
     const size_t n = (size_t)std::max<int64_t>(cs.n_total, 1);
     fill_cov_kernel<D, Real><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cs.cov_knn.as<Real>(), n, Real(0));
-    fill_cov_kernel<D, Real><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cs.cov_nn.as<Real>(), n, Real(0));
-    h->launches += 2;
+    if (!cs.shared) fill_cov_kernel<D, Real><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cs.cov_nn.as<Real>(), n, Real(0));
+    h->launches += cs.shared ? 1 : 2;
     CU(cudaGetLastError());
     return 0;
 }
@@ -497,16 +503,15 @@ int objective_args(gicpContext* h, ObjArgs<Real>& a, int& blocks_per_pair, bool 
     CloudSet &S = h->src, &T = h->tgt;
     if (!S.ready || !T.ready) return fail("set source and target first");
     if (S.n_clouds != T.n_clouds) return fail("source has %d clouds, target %d", S.n_clouds, T.n_clouds);
-    a.src_meta = S.nn.meta.as<CloudMeta>();
-    a.src_spts = S.nn.spts.as<PRec<Real>>();
-    a.src_cov = S.cov_nn.as<Real>();
-    a.src_perm = S.nn.perm.as<int>();
-    a.tgt_meta = T.nn.meta.as<CloudMeta>();
-    a.tgt_cell_start = T.nn.cell_start.as<int>();
-    a.tgt_lut = T.nn.lut.as<int>();
-    a.tgt_spts = T.nn.spts.as<PRec<Real>>();
-    a.tgt_cov = T.cov_nn.as<Real>();
-    a.tgt_perm = T.nn.perm.as<int>();
+    a.src_meta = S.nng().meta.as<CloudMeta>();
+    a.src_spts = S.nng().spts.as<PRec<Real>>();
+    a.src_cov = S.covnn().as<Real>();
+    a.tgt_meta = T.nng().meta.as<CloudMeta>();
+    a.tgt_cell_start = T.nng().cell_start.as<int>();
+    a.tgt_lut = T.nng().lut.as<int>();
+    a.tgt_spts = T.nng().spts.as<PRec<Real>>();
+    a.tgt_cov = T.covnn().as<Real>();
+    a.tgt_inv_perm = T.nng().inv_perm.as<int>();
     a.match = nullptr;
     a.use_prev = 0;
     CU(h->state.ensure((size_t)S.n_clouds * sizeof(PairState)));

@@ -124,16 +124,14 @@ __global__ void __launch_bounds__(256) cell_key_kernel(const Real* __restrict__ 
     atomicAdd(&cell_count[cell], 1);
 }
 
-// grid (blocks, n_clouds): sorted position s -> record {coords, idx}; idx is the cloud-local index of
-// the point in the caller's array (k-NN grids: it is the tie-break key and addresses the raw
-// coordinates) or, when `perm` is given (1-NN grids), the sorted position itself, with
-// perm[s] = cloud-local index kept on the side.  inv_perm[global row] = s.
+// grid (blocks, n_clouds): sorted position s -> record {coords, idx}; idx is the cloud-local index of the point in
+// the caller's array (the tie-break key of every search, and it addresses the raw coordinates).
+// inv_perm[global row] = s maps an input row back to its sorted position.
 template <int D, typename Real>
 __global__ void __launch_bounds__(256) gather_sorted_kernel(const Real* __restrict__ pts,
                                                             const CloudMeta* __restrict__ meta,
                                                             const int* __restrict__ sorted_vals,
-                                                            PRec<Real>* __restrict__ spts, int* __restrict__ inv_perm,
-                                                            int* __restrict__ perm) {
+                                                            PRec<Real>* __restrict__ spts, int* __restrict__ inv_perm) {
     const CloudMeta m = meta[blockIdx.y];
     const int s = m.pt_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= m.pt_end) return;
@@ -142,10 +140,9 @@ __global__ void __launch_bounds__(256) gather_sorted_kernel(const Real* __restri
     r.x = pts[(size_t)g * D + 0];
     r.y = pts[(size_t)g * D + 1];
     r.z = (D == 3) ? pts[(size_t)g * D + (D - 1)] : Real(0);
-    r.idx = perm ? s : g - m.pt_begin;
+    r.idx = g - m.pt_begin;
     spts[s] = r;
-    if (inv_perm) inv_perm[g] = s;
-    if (perm) perm[s] = g - m.pt_begin;
+    inv_perm[g] = s;
 }
 
 // grid (3 * GICP_LUT_N / 256, n_clouds): per-axis Morton spread tables, code(x,y,z) = lx[x] | ly[y] | lz[z]

@@ -34,10 +34,9 @@ template <typename Real> struct ObjArgs {
     const CloudMeta* tgt_meta;
     const int* tgt_cell_start;
     const int* tgt_lut;
-    const PRec<Real>* tgt_spts;   // records carry their own sorted position in .idx
+    const PRec<Real>* tgt_spts;   // records carry the cloud-local input index in .idx (tie-break key)
     const Real* tgt_cov;
-    const int* src_perm;          // sorted position -> cloud-local input index
-    const int* tgt_perm;
+    const int* tgt_inv_perm;      // input row (global) -> sorted position
     int* match;                   // [n_src_total], source nn order: matched target position or -1.  Written by
                                   // correspond_kernel, read by accumulate_kernel; with use_prev the previous
                                   // iteration's match bounds the next search
@@ -167,13 +166,15 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
         //      outer iteration gives an upper bound on the new nearest distance, so only the cells
         //      that intersect the ball of that radius around p' are searched (still exact). ----
         double bestd = d2cap;
-        int bestpos = -1;
+        int bestidx = -1;      // cloud-local input index of the best target point so far (-1: none)
+        int prevpos = -1;      // sorted position of the previous iteration's match when it seeds the search
+        int previdx = -1;
         if (a.use_prev) {
             const int pm = a.match[s];
             if (pm >= 0) {
                 const PRec<Real> qo = a.tgt_spts[pm];
                 const double e2 = exact_d2((double)qo.x - pp[0], (double)qo.y - pp[1], (double)qo.z - pp[2]);
-                if (e2 <= d2cap) { bestd = e2; bestpos = pm; }
+                if (e2 <= d2cap) { bestd = e2; bestidx = (int)qo.idx; prevpos = pm; previdx = bestidx; }
             }
         }
         const float fx = (float)pp[0], fy = (float)pp[1], fz = (float)pp[2];
@@ -203,11 +204,10 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
             }
             if (pass) {
                 if (sizeof(Real) == 4) e2 = exact_d2((double)c.x - pp[0], (double)c.y - pp[1], (double)c.z - pp[2]);
-                const int cpos = (int)c.idx;
+                const int cidx = (int)c.idx;
                 // exact ties (same float64 distance) go to the lower input index, like the oracle
-                if (e2 < bestd || (e2 == bestd && bestpos >= 0 && cpos != bestpos &&
-                                   a.tgt_perm[cpos] < a.tgt_perm[bestpos])) {
-                    bestd = e2; bestpos = cpos;
+                if (e2 < bestd || (e2 == bestd && bestidx >= 0 && cidx < bestidx)) {
+                    bestd = e2; bestidx = cidx;
                     thr32 = filter_thr(bestd);
                 }
             }
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
         const int y0 = max(mylo[1], 0), y1 = min(myhi[1], mt.dims[1] - 1);
         const int z0 = max(mylo[2], 0), z1 = min(myhi[2], mt.dims[2] - 1);
         const int ncell = max(x1 - x0 + 1, 0) * max(y1 - y0 + 1, 0) * max(z1 - z0 + 1, 0);
-        const bool tracked = !skip && bestpos >= 0 && ncell <= a.track_max_cells;
+        const bool tracked = !skip && bestidx >= 0 && ncell <= a.track_max_cells;
         // a tracked lane examines every point of the cell box [mylo, myhi]; everything outside that box is
         // at least `rad32` away (distance from p' to the nearest box face that has cells behind it)
         float rad32 = INFINITY;
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
                     if (sc[i] + rho < mt.dims[i] - 1) cover = fmin(cover, mt.origin[i] + (sc[i] + rho + 1) * mt.h - pp[i]);
                 }
                 cover *= (1.0 - 1e-9);
-                if ((bestpos >= 0 && bestd <= cover * cover) || cover >= a.d_max) { shell_done = true; break; }
+                if ((bestidx >= 0 && bestd <= cover * cover) || cover >= a.d_max) { shell_done = true; break; }
             }
         }
         // ---- phase B: warp-cooperative search through the TMA stage (what the shells could not settle).
@@ -342,9 +342,12 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
             }
         }
         if (!valid || skip) continue;
-        const double dist = (bestpos >= 0) ? sqrt(bestd) : INFINITY;
-        const bool matched = (bestpos >= 0) && !(dist > a.d_max);  // gicp.py:136 rejects d > d_max
-        a.match[s] = matched ? bestpos : -1;
+        const double dist = (bestidx >= 0) ? sqrt(bestd) : INFINITY;
+        const bool matched = (bestidx >= 0) && !(dist > a.d_max);  // gicp.py:136 rejects d > d_max
+        // the match is kept as the target's sorted position (what K3b gathers by): one look-up when it changed
+        int bestpos = -1;
+        if (matched) bestpos = (bestidx == previdx) ? prevpos : a.tgt_inv_perm[mt.pt_begin + bestidx];
+        a.match[s] = bestpos;
         if (a.slack) {
             float sl = 0.f;
             if (tracked && matched) {
@@ -358,8 +361,8 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
             a.slack[s] = sl;
         }
         if (a.out_idx || a.out_dist) {
-            const size_t out_row = (size_t)ms.pt_begin + (size_t)a.src_perm[s];
-            if (a.out_idx) a.out_idx[out_row] = matched ? a.tgt_perm[bestpos] : -1;
+            const size_t out_row = (size_t)ms.pt_begin + (size_t)p.idx;
+            if (a.out_idx) a.out_idx[out_row] = matched ? bestidx : -1;
             if (a.out_dist) a.out_dist[out_row] = dist;
         }
     }
@@ -463,7 +466,7 @@ __global__ void __launch_bounds__(OBJ_THREADS, 4) accumulate_kernel(const ObjArg
         g_cur = gather(m_next, it + 1);   // in flight during this iteration's arithmetic
         m_cur = m_next;
         m_next = load_match(it + 2);
-        const size_t out_row = (size_t)ms.pt_begin + (size_t)(a.out_W ? a.src_perm[s] : 0);
+        const size_t out_row = (size_t)ms.pt_begin + (size_t)g.p.idx;
         if (bestpos < 0) {
             if (a.out_W) {
                 for (int i = 0; i < D * D; ++i) a.out_W[out_row * D * D + i] = 0.0;
