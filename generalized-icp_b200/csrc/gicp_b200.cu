@@ -132,7 +132,7 @@ struct gicpContext {
     gicpParams prm;
     CloudSet src, tgt;
     DevBuf keys, keys_alt, vals, vals_alt, cub_tmp, cell_count, bbox_part;
-    DevBuf state, partial, red, T_dev, n_active, prev_match, slack, ovf_count, ovf_list;
+    DevBuf state, partial, partial2, red, T_dev, n_active, prev_match, slack, ovf_count, ovf_list;
     int* h_poll = nullptr;  // pinned
     cudaStream_t last_stream = nullptr;   // stream of the last gicpSet*/gicpRegister call (gicpPromoteTargetToSource has none)
     int64_t launches = 0;
@@ -603,6 +603,14 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
     sa.d_inliers = d_inliers;
     sa.n_active = h->n_active.as<int>();
     const dim3 ogrid(bpp, np);
+    // thousands of block partials per pair (one large pair): fold them 64 to 1 before the one-warp sum of K4
+    const bool presum = bpp > 2 * PRESUM_SPAN;
+    const int bpp2 = (bpp + PRESUM_SPAN - 1) / PRESUM_SPAN;
+    if (presum) {
+        CU(h->partial2.ensure((size_t)np * bpp2 * Dim<D>::NRED * sizeof(double)));
+        sa.partial = h->partial2.as<double>();
+        sa.blocks_per_pair = bpp2;
+    }
     // the search runs on smaller blocks than the accumulation (its work per point is uneven: better balance and
     // a shorter tail), the accumulation keeps the longer per-thread pipeline
     ObjArgs<Real> oc = oa;
@@ -626,6 +634,11 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
             accumulate_kernel<D, Real><<<ogrid, OBJ_THREADS, 0, st>>>(oa);
         }
         ProfScope prof(h, GICP_STAGE_SOLVE, st);
+        if (presum) {
+            presum_kernel<D><<<dim3(bpp2, np), Dim<D>::NRED, 0, st>>>(h->partial.as<double>(), bpp, h->partial2.as<double>(),
+                                                                    bpp2, h->state.as<PairState>());
+            h->launches += 1;
+        }
         if (sharded) {
             SolveArgs s1 = sa;
             s1.sum_out = h->red.as<double>();
@@ -795,7 +808,7 @@ int gicpDestroy(gicpHandle h) {
     h->src.release();
     h->tgt.release();
     DevBuf* bufs[] = {&h->keys, &h->keys_alt, &h->vals, &h->vals_alt, &h->cub_tmp, &h->cell_count, &h->bbox_part,
-                      &h->state, &h->partial, &h->red, &h->T_dev, &h->n_active, &h->prev_match, &h->slack, &h->ovf_count, &h->ovf_list};
+                      &h->state, &h->partial, &h->partial2, &h->red, &h->T_dev, &h->n_active, &h->prev_match, &h->slack, &h->ovf_count, &h->ovf_list};
     for (DevBuf* b : bufs) b->release();
     if (h->h_poll) cudaFreeHost(h->h_poll);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);

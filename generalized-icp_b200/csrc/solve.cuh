@@ -228,6 +228,27 @@ template <int D> __device__ inline void write_T(double* out, const PairState& st
 }
 
 constexpr int SOLVE_WARPS = 4;
+constexpr int PRESUM_SPAN = 64;   // block partials folded into one row by presum_kernel
+
+// Large pairs have thousands of block partials per pair and K4 sums them with one warp: fold PRESUM_SPAN consecutive
+// rows into one first (fixed order: bitwise reproducible).  grid (ceil(blocks_per_pair / PRESUM_SPAN), n_pairs), NRED threads.
+template <int D>
+__global__ void presum_kernel(const double* __restrict__ partial, int blocks_per_pair, double* __restrict__ out,
+                              int out_per_pair, const PairState* __restrict__ state) {
+    constexpr int NRED = Dim<D>::NRED;
+    const int pair = blockIdx.y;
+    if (state[pair].status != PAIR_ACTIVE) return;
+    const int b0 = blockIdx.x * PRESUM_SPAN, b1 = min(b0 + PRESUM_SPAN, blocks_per_pair);
+    const double* p = partial + ((size_t)pair * blocks_per_pair + b0) * NRED + threadIdx.x;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;   // four chains, combined in a fixed order
+    int b = b0;
+    for (; b + 4 <= b1; b += 4) {
+        s0 += p[0]; s1 += p[NRED]; s2 += p[2 * NRED]; s3 += p[3 * NRED];
+        p += 4 * NRED;
+    }
+    for (; b < b1; ++b) { s0 += p[0]; p += NRED; }
+    out[((size_t)pair * out_per_pair + blockIdx.x) * NRED + threadIdx.x] = (s0 + s1) + (s2 + s3);
+}
 
 template <int D>
 __global__ void __launch_bounds__(SOLVE_WARPS * 32) solve_kernel(const SolveArgs a) {

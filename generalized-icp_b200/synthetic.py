@@ -60,12 +60,14 @@ CONFIG5_PARAMS = dict(k=20, max_distance_nearest_neighbors=1.8, max_distance_cor
 
 
 def patches3d_batch_device(n_pairs, n=32_768, n_patches=16, cube=40.0, patch=30.0, sigma=0.02,
-                           max_rot_deg=2.0, max_trans=0.5, seed=0, device="cuda", chunk=256):
+                           max_rot_deg=2.0, max_trans=0.5, seed=0, device="cuda", chunk=256, first_pair=0):
     """Config-4 batch generated in HBM: (src, tgt) float32 (n_pairs*n, 3), CSR
     offsets (n_pairs+1,) int64 (identical for both sides) and the ground-truth
     4x4 per pair.  Same distribution as :func:`patches3d_pair`; the random
     stream is torch's Philox generator seeded with ``seed`` (per-chunk), so a
-    sample of pairs can be copied back for the CPU oracle."""
+    sample of pairs can be copied back for the CPU oracle.  ``first_pair``: the batch is pairs
+    [first_pair, first_pair + n_pairs) of one job-wide sequence (a rank's share of a batch that is partitioned
+    over GPUs); with ``first_pair`` a multiple of ``chunk`` every rank count reproduces the same job."""
     import torch
 
     g = torch.Generator(device=device)
@@ -74,7 +76,7 @@ def patches3d_batch_device(n_pairs, n=32_768, n_patches=16, cube=40.0, patch=30.
     Ts = torch.empty((n_pairs, 4, 4), dtype=torch.float64, device=device)
     for c0 in range(0, n_pairs, chunk):
         b = min(chunk, n_pairs - c0)
-        g.manual_seed(seed * 1_000_003 + c0)
+        g.manual_seed(seed * 1_000_003 + first_pair + c0)
         centres = torch.empty((b, n_patches, 3), device=device).uniform_(0.25 * cube, 0.75 * cube, generator=g)
         frames, _ = torch.linalg.qr(torch.randn((b, n_patches, 3, 3), device=device, generator=g))
         axis = torch.randn((b, 3), device=device, dtype=torch.float64, generator=g)
