@@ -3,6 +3,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX: ranges per stage for nsys / ncu timelines
 
 #include <algorithm>
 #include <cstdarg>
@@ -74,6 +75,7 @@ struct Grid {
 struct CloudSet {
     const void* raw = nullptr;
     std::vector<int64_t> offsets;
+    std::vector<int> off32;   // staging copy of the offsets for the asynchronous upload (must outlive the call)
     int n_clouds = 0;
     int64_t n_total = 0;
     int max_n = 0;
@@ -133,7 +135,9 @@ struct gicpContext {
     CloudSet src, tgt;
     DevBuf keys, keys_alt, vals, vals_alt, cub_tmp, cell_count, bbox_part;
     DevBuf state, partial, partial2, red, T_dev, n_active, prev_match, slack, ovf_count, ovf_list;
-    int* h_poll = nullptr;  // pinned
+    static constexpr int NPOLL = 8;
+    int* h_poll = nullptr;  // pinned [NPOLL]: progress polls in flight
+    cudaEvent_t poll_ev[NPOLL] = {};
     cudaStream_t last_stream = nullptr;   // stream of the last gicpSet*/gicpRegister call (gicpPromoteTargetToSource has none)
     int64_t launches = 0;
     // per-stage CUDA-event timing (off by default): stage ids in include/gicp_b200.h
@@ -159,11 +163,15 @@ namespace {
 
 int ns_of(int dim) { return dim * (dim + 1) / 2; }
 
+const char* const kStageNames[GICP_N_STAGES] = {"gicp:grid_build", "gicp:knn_cov", "gicp:correspond", "gicp:accumulate",
+                                                 "gicp:solve"};
+
 struct ProfScope {
     gicpContext* h;
     cudaStream_t st;
     cudaEvent_t b = nullptr;
     ProfScope(gicpContext* h_, int stage, cudaStream_t st_) : h(h_), st(st_) {
+        nvtxRangePushA(kStageNames[stage]);   // a no-op unless a profiler is attached
         if (!h->prof_on) return;
         cudaEvent_t a = h->prof_event();
         b = h->prof_event();
@@ -172,6 +180,7 @@ struct ProfScope {
     }
     ~ProfScope() {
         if (b) cudaEventRecord(b, st);
+        nvtxRangePop();
     }
 };
 
@@ -419,7 +428,8 @@ int set_cloud(gicpContext* h, int which, const void* d_points, const int64_t* h_
     if (h_offsets[0] != 0) return fail("offsets[0] must be 0");
     if (cs.n_total >= (1LL << 31) - 1024) return fail("more than 2^31 points in one batch");
     cs.max_n = 0;
-    std::vector<int> off32(n_clouds + 1);
+    std::vector<int>& off32 = cs.off32;
+    off32.resize(n_clouds + 1);
     for (int i = 0; i <= n_clouds; ++i) {
         off32[i] = (int)h_offsets[i];
         if (i && h_offsets[i] < h_offsets[i - 1]) return fail("offsets must be non-decreasing");
@@ -427,8 +437,9 @@ int set_cloud(gicpContext* h, int which, const void* d_points, const int64_t* h_
     }
     if (cs.n_total > 0 && !d_points) return fail("null point array");
     CU(cs.d_offsets.ensure(off32.size() * sizeof(int)));
+    // no stream synchronisation here: a copy from pageable memory is staged by the driver before the call returns,
+    // and the staging vector lives in the handle
     CU(cudaMemcpyAsync(cs.d_offsets.p, off32.data(), off32.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    CU(cudaStreamSynchronize(st));  // off32 is a stack-lifetime staging buffer
 
     const double h_knn = auto_knn_cell(h);
     const double h_nn = auto_nn_cell(h);
@@ -564,7 +575,8 @@ int ensure_state(gicpContext* h, const double* h_T0, double* d_T, double* d_T_hi
         d_T0 = h->T_dev.as<double>();
     }
     init_state_kernel<D><<<(np + 127) / 128, 128, 0, st>>>(h->state.as<PairState>(), d_T0, h->tgt.knn.bbox.as<double>(), np,
-                                                           d_T, d_T_hist, h->prm.max_iterations, d_n_outer, d_converged);
+                                                           d_T, d_T_hist, h->prm.max_iterations, d_n_outer, d_converged,
+                                                           h->n_active.as<int>());
     h->launches += 1;
     CU(cudaGetLastError());
     return 0;
@@ -579,8 +591,6 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
     const int np = h->src.n_clouds;
     h->last_stream = st;
     if (ensure_state<D, Real>(h, h_T0, d_T, d_T_hist, d_n_outer, d_converged, st)) return 1;
-    CU(cudaMemcpyAsync(h->n_active.p, &np, sizeof(int), cudaMemcpyHostToDevice, st));
-    CU(cudaStreamSynchronize(st));
     // last iteration's match per source point (bounds the next search); -1 = none yet
     CU(cudaMemsetAsync(h->prev_match.p, 0xFF, (size_t)std::max<int64_t>(h->src.n_total, 1) * sizeof(int), st));
     CU(cudaMemsetAsync(h->slack.p, 0, (size_t)std::max<int64_t>(h->src.n_total, 1) * sizeof(float), st));
@@ -622,9 +632,26 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
     const dim3 cgrid(bpp * (oa.ppt / oc.ppt), np);
     const int sgrid = (np + SOLVE_WARPS - 1) / SOLVE_WARPS;
     const bool sharded = h->comm && np == 1;
-    *h->h_poll = np;
-    const int poll_every = 2;
+    // Progress polls (4 bytes each, the only host<->device traffic inside the loop).  A single-process registration
+    // does not wait for them: the count of still-active pairs is copied to pinned memory after every iteration and
+    // looked at (cudaEventQuery) before later iterations are launched, so the host runs a few iterations ahead and the
+    // GPU never idles on a round trip; an iteration launched after everything converged is a no-op (every block
+    // returns on the pair's status).  With a communicator every rank must issue the same all-reduces, so the sharded
+    // mode keeps a blocking poll on a fixed schedule (all ranks see the same count: they solve bit-identical forms).
+    constexpr int LOOK = 3;
+    int issued = 0, checked = 0;
     for (int it = 0; it < h->prm.max_iterations; ++it) {
+        bool done = false;
+        while (checked < issued && !done) {
+            const int slot = checked % gicpContext::NPOLL;
+            cudaError_t q = (sharded || issued - checked > LOOK) ? cudaEventSynchronize(h->poll_ev[slot])
+                                                                 : cudaEventQuery(h->poll_ev[slot]);
+            if (q == cudaErrorNotReady) { cudaGetLastError(); break; }
+            CU(q);
+            done = h->h_poll[slot] <= 0;
+            ++checked;
+        }
+        if (done) break;
         {
             ProfScope prof(h, GICP_STAGE_CORRESPOND, st);
             correspond_kernel<D, Real><<<cgrid, OBJ_THREADS, obj_smem(oc.ppt), st>>>(oc);
@@ -633,32 +660,34 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
             ProfScope prof(h, GICP_STAGE_ACCUMULATE, st);
             accumulate_kernel<D, Real><<<ogrid, OBJ_THREADS, 0, st>>>(oa);
         }
-        ProfScope prof(h, GICP_STAGE_SOLVE, st);
-        if (presum) {
-            presum_kernel<D><<<dim3(bpp2, np), Dim<D>::NRED, 0, st>>>(h->partial.as<double>(), bpp, h->partial2.as<double>(),
-                                                                    bpp2, h->state.as<PairState>());
-            h->launches += 1;
+        {
+            ProfScope prof(h, GICP_STAGE_SOLVE, st);
+            if (presum) {
+                presum_kernel<D><<<dim3(bpp2, np), Dim<D>::NRED, 0, st>>>(h->partial.as<double>(), bpp, h->partial2.as<double>(),
+                                                                        bpp2, h->state.as<PairState>());
+                h->launches += 1;
+            }
+            if (sharded) {
+                SolveArgs s1 = sa;
+                s1.sum_out = h->red.as<double>();
+                solve_kernel<D><<<sgrid, SOLVE_WARPS * 32, 0, st>>>(s1);
+                int rc = g_nccl.AllReduce(h->red.p, h->red.p, (size_t)Dim<D>::NRED, NCCL_FLOAT64, NCCL_SUM, h->comm, st);
+                if (rc) return fail("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+                SolveArgs s2 = sa;
+                s2.partial = h->red.as<double>();
+                s2.blocks_per_pair = 1;
+                solve_kernel<D><<<sgrid, SOLVE_WARPS * 32, 0, st>>>(s2);
+                h->launches += 4;
+            } else {
+                solve_kernel<D><<<sgrid, SOLVE_WARPS * 32, 0, st>>>(sa);
+                h->launches += 3;
+            }
         }
-        if (sharded) {
-            SolveArgs s1 = sa;
-            s1.sum_out = h->red.as<double>();
-            solve_kernel<D><<<sgrid, SOLVE_WARPS * 32, 0, st>>>(s1);
-            int rc = g_nccl.AllReduce(h->red.p, h->red.p, (size_t)Dim<D>::NRED, NCCL_FLOAT64, NCCL_SUM, h->comm, st);
-            if (rc) return fail("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
-            SolveArgs s2 = sa;
-            s2.partial = h->red.as<double>();
-            s2.blocks_per_pair = 1;
-            solve_kernel<D><<<sgrid, SOLVE_WARPS * 32, 0, st>>>(s2);
-            h->launches += 4;
-        } else {
-            solve_kernel<D><<<sgrid, SOLVE_WARPS * 32, 0, st>>>(sa);
-            h->launches += 3;
-        }
-        if ((it + 1) % poll_every == 0 || it + 1 == h->prm.max_iterations) {
-            // progress poll: 4 bytes, the only host<->device traffic inside the loop
-            CU(cudaMemcpyAsync(h->h_poll, h->n_active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            if (*h->h_poll <= 0) break;
+        if (!sharded || (it + 1) % 2 == 0) {
+            const int slot = issued % gicpContext::NPOLL;
+            CU(cudaMemcpyAsync(h->h_poll + slot, h->n_active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(cudaEventRecord(h->poll_ev[slot], st));
+            ++issued;
         }
     }
     CU(cudaGetLastError());
@@ -796,7 +825,8 @@ int gicpCreate(gicpHandle* out, int device, int dim, int storage) {
     h->dim = dim;
     h->storage = storage;
     gicpDefaultParams(&h->prm);
-    CU(cudaMallocHost(&h->h_poll, sizeof(int)));
+    CU(cudaMallocHost(&h->h_poll, gicpContext::NPOLL * sizeof(int)));
+    for (int i = 0; i < gicpContext::NPOLL; ++i) CU(cudaEventCreateWithFlags(&h->poll_ev[i], cudaEventDisableTiming));
     *out = h;
     return 0;
 }
@@ -811,6 +841,7 @@ int gicpDestroy(gicpHandle h) {
                       &h->state, &h->partial, &h->partial2, &h->red, &h->T_dev, &h->n_active, &h->prev_match, &h->slack, &h->ovf_count, &h->ovf_list};
     for (DevBuf* b : bufs) b->release();
     if (h->h_poll) cudaFreeHost(h->h_poll);
+    for (cudaEvent_t e : h->poll_ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
     return 0;

@@ -183,7 +183,11 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
         const float c1 = 5e-7f * Pf * 1.0001f;
         auto filter_thr = [&](double bd) {
             const float b = __double2float_ru(bd);
-            return fmaf(b, 1.000002f, c1 * sqrtf(b)) + 1e-30f;
+            // sqrt(b) through the reciprocal-square-root unit (2 instructions instead of the IEEE sequence; it is
+            // re-evaluated on every improvement of the best distance): 2 ulp of error, covered by the 1.0001 in c1
+            const float bb = fmaxf(b, 1e-30f);
+            const float sq = bb * rsqrtf(bb);               // sqrt(max(b, 1e-30)) >= sqrt(b): never under the bound
+            return fmaf(b, 1.000002f, c1 * sq) + 1e-30f;
         };
         float thr32 = filter_thr(bestd);
         float m1 = INFINITY, m2 = INFINITY;   // two smallest fp32 squared distances seen (slack of the next iterations)

@@ -342,8 +342,9 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) solve_kernel(const SolveArgs
 template <int D>
 __global__ void init_state_kernel(PairState* state, const double* T0, const double* tgt_bbox, int n_pairs,
                                   double* d_T, double* d_T_hist, int max_iterations, int* d_n_outer,
-                                  int* d_converged) {
+                                  int* d_converged, int* n_active) {
     const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair == 0 && n_active) *n_active = n_pairs;   // pairs still iterating (K4 counts it down, the host polls it)
     if (pair >= n_pairs) return;
     PairState st;
     for (int i = 0; i < 9; ++i) st.R[i] = (i % 4 == 0) ? 1.0 : 0.0;
