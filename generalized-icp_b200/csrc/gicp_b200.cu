@@ -217,7 +217,7 @@ int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, cudaStrea
     ProfScope prof(h, GICP_STAGE_GRID, st);
 
     bbox_partial_kernel<D, Real><<<dim3(chunks, nc), BBOX_THREADS, 0, st>>>(pts, offs, h->bbox_part.as<double>(), chunks);
-    grid_meta_kernel<D><<<(nc + 127) / 128, 128, 0, st>>>(h->bbox_part.as<double>(), chunks, offs, nc, h_target, budget,
+    grid_meta_kernel<D><<<(nc + 3) / 4, 128, 0, st>>>(h->bbox_part.as<double>(), chunks, offs, nc, h_target, budget,
                                                           g.meta.as<CloudMeta>(), g.bbox.as<double>());
     CU(g.lut.ensure((size_t)nc * 3 * GICP_LUT_N * sizeof(int)));
     morton_lut_kernel<<<dim3(3 * GICP_LUT_N / 256, nc), 256, 0, st>>>(g.meta.as<CloudMeta>(), g.lut.as<int>());

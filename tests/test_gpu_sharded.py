@@ -1,6 +1,7 @@
 """Sharded single pair (BASELINE config 5 shape, small): every rank holds both clouds, computes its
 slice of the covariances / of the per-iteration reduction; one NCCL all-gather + one all-reduce per
-outer iteration inside libgicp_b200.so.  Needs >= 2 GPUs (gpurun --gpus 2); skipped otherwise."""
+outer iteration inside libgicp_b200.so.  Needs >= 2 GPUs (gpurun --gpus 2 / 4 / 8); the sizes the box does not have are skipped.
+Logs of the 2- and 8-GPU runs are kept under profiles/ (pytest_sharded_*_r02.log)."""
 import os
 import socket
 
@@ -40,10 +41,11 @@ def _worker(rank, world, port, src, tgt, prm, out):
     dist.destroy_process_group()
 
 
-def test_sharded_source_matches_single_gpu():
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_source_matches_single_gpu(world):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     from generalized_icp_b200 import synthetic
     from generalized_icp_b200.engine import GicpEngine
@@ -57,7 +59,6 @@ def test_sharded_source_matches_single_gpu():
     T_ref, n_ref = ref.T[0].cpu().numpy(), int(ref.n_outer[0])
     cov_ref = eng.covariances(1).cpu().numpy()
     del eng
-    world = 2
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), src, tgt, prm, out), nprocs=world, join=True)
@@ -67,4 +68,5 @@ def test_sharded_source_matches_single_gpu():
         # the sum over ranks associates differently from the single-GPU block order: 1e-9 relative
         assert np.abs(T - T_ref).max() < 1e-7
         assert np.array_equal(cov, cov_ref)          # all-gathered covariances are bit-identical
-    assert np.array_equal(out[0][0], out[1][0])      # every rank solves the same reduced form
+    for r in range(1, world):
+        assert np.array_equal(out[0][0], out[r][0])  # every rank solves the same reduced form
