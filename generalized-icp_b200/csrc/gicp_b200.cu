@@ -193,6 +193,14 @@ int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, cudaStrea
         budget = 4096;  // Morton padding can cost up to 8x the occupied box
         while (budget < 8LL * cs.max_n) budget <<= 1;
     }
+    // Large batches: the table (memset + scan + 4 B per cell, per cloud set) is sized for one cell per point instead
+    // of eight - grid_meta_kernel then enlarges the cell edge by the few per cent that save the Morton bits (a 40 m
+    // cloud at 1.25 m cells needs 33-36 cells per axis = 2^18 padded; at 1.3-1.4 m it fits 2^15)
+    if (h->prm.max_cells_per_cloud <= 0) {
+        long long cap_total = 1LL << 30;   // default: no shrinking (measured: the larger cells cost K2 more than K1 gains)
+        if (getenv("GICP_CELL_TABLE_LOG2") && atoi(getenv("GICP_CELL_TABLE_LOG2")) > 0) cap_total = 1LL << atoi(getenv("GICP_CELL_TABLE_LOG2"));
+        while (budget * (long long)nc > cap_total && budget > 4096 && budget / 2 >= cs.max_n) budget >>= 1;
+    }
     if (budget * (long long)nc > (1LL << 30)) {
         budget = (1LL << 30) / nc;
         if (budget < 64) return fail("too many clouds for the cell table (%d)", nc);

@@ -102,7 +102,15 @@ __global__ void grid_meta_kernel(const double* __restrict__ part, int chunks, co
             if (bts > GICP_MAX_AXIS_BITS) ok = false;
         }
         if (ok && sum_bits <= 30 && (1LL << sum_bits) <= budget) break;
-        h *= 1.2599210498948732;  // doubles the cell volume in 3-D
+        // smallest enlargement that saves one Morton bit: the axis whose cell count is closest above a power of
+        // two gives way first (extent / 2^(bits - 1) is the edge at which that axis fits one bit less)
+        double h_next = INFINITY;
+        for (int c = 0; c < D; ++c) {
+            if (m.bits[c] < 1) continue;
+            const double hc = (hi[c] - lo[c]) / (double)(1 << (m.bits[c] - 1)) * (1.0 + 1e-9);
+            if (hc > h) h_next = fmin(h_next, hc);
+        }
+        h = (h_next < h * 1.2599210498948732) ? h_next : h * 1.2599210498948732;
     }
     for (int c = 0; c < 3; ++c) m.origin[c] = lo[c];
     m.cell_base = (int)((long long)cloud * budget);
