@@ -19,6 +19,7 @@
 #include "objective.cuh"
 #include "raycast.cuh"
 #include "solve.cuh"
+#include "fused.cuh"
 
 using namespace gicp;
 
@@ -224,6 +225,20 @@ int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, cudaStrea
     const int* offs = cs.d_offsets.as<int>();
     ProfScope prof(h, GICP_STAGE_GRID, st);
 
+    // small clouds (the reference's own workloads): the whole build of a cloud in one block, one launch
+    if (cs.max_n <= SMALL_GRID_MAX && budget <= (1LL << 20) && n > 0 &&
+        !(getenv("GICP_SMALL_GRID") && atoi(getenv("GICP_SMALL_GRID")) == 0)) {
+        CU(g.lut.ensure((size_t)nc * 3 * GICP_LUT_N * sizeof(int)));
+        small_grid_kernel<D, Real><<<nc, SMALL_GRID_THREADS, 0, st>>>(pts, offs, h_target, budget, g.meta.as<CloudMeta>(),
+                                                                      g.bbox.as<double>(), g.lut.as<int>(),
+                                                                      g.cell_start.as<int>(), g.spts.as<PRec<Real>>(),
+                                                                      g.inv_perm.as<int>(), 1);
+        h->launches += 1;
+        CU(cudaGetLastError());
+        g.built = true;
+        return 0;
+    }
+
     bbox_partial_kernel<D, Real><<<dim3(chunks, nc), BBOX_THREADS, 0, st>>>(pts, offs, h->bbox_part.as<double>(), chunks);
     grid_meta_kernel<D><<<(nc + 3) / 4, 128, 0, st>>>(h->bbox_part.as<double>(), chunks, offs, nc, h_target, budget,
                                                           g.meta.as<CloudMeta>(), g.bbox.as<double>());
@@ -361,7 +376,10 @@ int launch_knn(gicpContext* h, CloudSet& cs, int* d_idx, double* d_dist, cudaStr
     a.overflow_count = h->ovf_count.as<int>();
     a.overflow_list = h->ovf_list.as<int2>();
     a.overflow_cap = (int)std::min<long long>(n_chunks, INT_MAX);
-    const bool fast = a.k + 8 <= knn_list_cap<Real>();
+    // latency mode (a few small clouds): the general kernel alone - one launch, no overflow hand-over
+    const bool latency_mode = cs.max_n <= SMALL_GRID_MAX && cs.n_total <= 65536 &&
+                              !(getenv("GICP_SMALL_GRID") && atoi(getenv("GICP_SMALL_GRID")) == 0);
+    const bool fast = a.k + 8 <= knn_list_cap<Real>() && !latency_mode;
     const size_t smem_g = 128 + (size_t)KNN_WARPS * KNN_WARP_SMEM;
     const size_t smem_h = 128 + (size_t)KNN_WARPS * KNN_HIST_WARP_SMEM;
     ProfScope prof(h, GICP_STAGE_KNN_COV, st);
@@ -620,6 +638,23 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
     sa.d_T_hist = d_T_hist;
     sa.d_inliers = d_inliers;
     sa.n_active = h->n_active.as<int>();
+    // Small pairs (every source cloud fits one block): the whole outer loop in one launch (fused.cuh).  Not with a
+    // communicator (the all-reduce sits between the stages) and not while per-stage timing is on.
+    const bool sharded_pair = h->comm && np == 1;
+    if (!sharded_pair && !h->prof_on && h->src.max_n <= OBJ_THREADS * OBJ_MAX_PPT &&
+        !(getenv("GICP_FUSED_LOOP") && atoi(getenv("GICP_FUSED_LOOP")) == 0)) {
+        oa.ppt = std::max(1, (h->src.max_n + OBJ_THREADS - 1) / OBJ_THREADS);
+        oa.blocks_per_pair = 1;
+        sa.blocks_per_pair = 1;
+        sa.n_active = nullptr;   // nobody polls
+        const size_t smem = obj_smem(oa.ppt);
+        CU(cudaFuncSetAttribute(register_loop_kernel<D, Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ProfScope prof(h, GICP_STAGE_CORRESPOND, st);
+        register_loop_kernel<D, Real><<<np, OBJ_THREADS, smem, st>>>(oa, sa);
+        h->launches += 1;
+        CU(cudaGetLastError());
+        return 0;
+    }
     const dim3 ogrid(bpp, np);
     // thousands of block partials per pair (one large pair): fold them 64 to 1 before the one-warp sum of K4
     const bool presum = bpp > 2 * PRESUM_SPAN;

@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Rea
         //      the lane's k-th distance; blocks beyond every lane's bound are not staged ----
         float prov32 = r2cap32;
         float lim = mine ? r2cap32 : -1.0f;   // candidates beyond the lane's provisional bound are not binned
+        int seen = 0;
         for (int rho = 0; rho <= rho_max; ++rho) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) { lo[c] = max(qlo[c] - rho, 0); hi[c] = min(qhi[c] + rho, m.dims[c] - 1); }
@@ -335,15 +336,15 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Rea
                     const int g1 = max((int)(__float_as_uint(e1) >> 20) - ubase, 0);
                     const int g2 = max((int)(__float_as_uint(e2) >> 20) - ubase, 0);
                     const int g3 = max((int)(__float_as_uint(e3) >> 20) - ubase, 0);
-                    if (e0 <= lim) hist[g0 * 32 + lane] += 1;
-                    if (e1 <= lim) hist[g1 * 32 + lane] += 1;
-                    if (e2 <= lim) hist[g2 * 32 + lane] += 1;
-                    if (e3 <= lim) hist[g3 * 32 + lane] += 1;
+                    if (e0 <= lim) { hist[g0 * 32 + lane] += 1; ++seen; }
+                    if (e1 <= lim) { hist[g1 * 32 + lane] += 1; ++seen; }
+                    if (e2 <= lim) { hist[g2 * 32 + lane] += 1; ++seen; }
+                    if (e3 <= lim) { hist[g3 * 32 + lane] += 1; ++seen; }
                 }
                 for (; j < n; ++j) {
                     const float e0 = dist32(w[j]);
                     const int g0 = max((int)(__float_as_uint(e0) >> 20) - ubase, 0);
-                    if (e0 <= lim) hist[g0 * 32 + lane] += 1;
+                    if (e0 <= lim) { hist[g0 * 32 + lane] += 1; ++seen; }
                 }
             }, [&](int x0, int y0, int z0, int x1, int y1, int z1) {
                 return mine && cell_box_dist2(m, pad, (float)mx, (float)my, (float)mz, x0, y0, z0, x1, y1, z1) <= prov32;
@@ -352,16 +353,16 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_hist_kernel(const KnnArgs<Rea
             for (int c = 0; c < 3; ++c) { plo[c] = lo[c]; phi[c] = hi[c]; }
             // bin that holds the k-th candidate -> bound on the k-th neighbour distance.  (A counter
             // that wrapped at 256 only makes the bound larger, never wrong.)
-            // (no separate count of the binned candidates: fewer than k of them leave kb at the last bin)
             int kb = KNN_BINS - 1;
-            {
+            bool have = false;
+            if (seen >= a.k) {
                 int cum = 0;
                 for (int b = 0; b < KNN_BINS; ++b) {
                     cum += hist[b * 32 + lane];
                     if (cum >= a.k) { kb = b; break; }
                 }
+                have = kb < KNN_BINS - 1;
             }
-            const bool have = kb < KNN_BINS - 1;
             // every candidate of bins <= kb has d2 < edge2 (exact: bin edges are float bit patterns)
             const float edge2 = have ? __uint_as_float((unsigned)(ubase + kb + 1) << 20) : r2cap32;
             prov32 = fminf(prov32, edge2);

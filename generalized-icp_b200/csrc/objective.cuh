@@ -58,9 +58,12 @@ template <typename Real> struct ObjArgs {
     int shell_search;         // untracked lanes search per-lane shells before the cooperative phase
 };
 
+// One block of the search: points [bx * ppt * OBJ_THREADS, ...) of pair `pair`.  `ws` is the warp's TMA stage
+// (buffer, mbarrier, phase); it is carried by the caller so that the fused registration loop (register_loop_kernel)
+// can call this once per outer iteration on one initialised mbarrier.
 template <int D, typename Real>
-__global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<Real> a) {
-    const int pair = blockIdx.y;
+__device__ __forceinline__ void correspond_block(const ObjArgs<Real>& a, const int pair, const int bx,
+                                                 WarpStage<Real>& ws, unsigned char* smem_raw) {
     const PairState st = a.state[pair];
     if (!a.ignore_status && st.status != PAIR_ACTIVE) return;
 
@@ -88,15 +91,7 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
     const double d2cap = a.d_max * a.d_max * (1.0 + 1e-9);
     const float pad = cell_box_pad(mt);
 
-    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpStage<Real> ws;
-    ws.buf = reinterpret_cast<PRec<Real>*>(smem_raw + 128 + warp * OBJ_STAGE_BYTES);
-    ws.bar = reinterpret_cast<uint64_t*>(smem_raw) + warp;
-    ws.phase = 0;
-    ws.cap = OBJ_STAGE_BYTES / (int)sizeof(PRec<Real>);
-    if (lane == 0) { mbar_init(ws.bar, 1); mbar_fence_init(); }
-    __syncwarp();
 
     // ---- pass 1 (tracking iterations): decide for every point of the block whether its match can have
     //      changed at all, and compact the ones that need a search into a dense work list, so that the
@@ -106,7 +101,7 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
     //      then, the same target point is still strictly the nearest. ----
     int* s_list = reinterpret_cast<int*>(smem_raw + 128 + (OBJ_THREADS / 32) * OBJ_STAGE_BYTES);   // [OBJ_THREADS * ppt]
     __shared__ int s_count;
-    const int blk_begin = begin + blockIdx.x * a.ppt * OBJ_THREADS;
+    const int blk_begin = begin + bx * a.ppt * OBJ_THREADS;
     const int blk_end = min(end, blk_begin + a.ppt * OBJ_THREADS);
     const bool compact = a.use_prev && a.slack != nullptr;
     if (threadIdx.x == 0) s_count = 0;
@@ -372,12 +367,33 @@ __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<R
     }
 }
 
+// the warp's TMA stage inside the block's dynamic shared memory (obj_smem() bytes); lane 0 initialises the mbarrier
+template <typename Real>
+__device__ __forceinline__ WarpStage<Real> obj_warp_stage(unsigned char* smem_raw) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpStage<Real> ws;
+    ws.buf = reinterpret_cast<PRec<Real>*>(smem_raw + 128 + warp * OBJ_STAGE_BYTES);
+    ws.bar = reinterpret_cast<uint64_t*>(smem_raw) + warp;
+    ws.phase = 0;
+    ws.cap = OBJ_STAGE_BYTES / (int)sizeof(PRec<Real>);
+    if (lane == 0) { mbar_init(ws.bar, 1); mbar_fence_init(); }
+    __syncwarp();
+    return ws;
+}
+
 template <int D, typename Real>
-__global__ void __launch_bounds__(OBJ_THREADS, 4) accumulate_kernel(const ObjArgs<Real> a) {
+__global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<Real> a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    WarpStage<Real> ws = obj_warp_stage<Real>(smem_raw);
+    correspond_block<D, Real>(a, blockIdx.y, blockIdx.x, ws, smem_raw);
+}
+
+// One block of the accumulation: points [bx * ppt * OBJ_THREADS, ...) of pair `pair` -> partial[pair][bx][NRED]
+template <int D, typename Real>
+__device__ __forceinline__ void accumulate_block(const ObjArgs<Real>& a, const int pair, const int bx) {
     using DD = Dim<D>;
     using AccT = Real;
     constexpr int NP = DD::NP, NS = DD::NS, NH = DD::NH, NQ = DD::NQ, NRED = DD::NRED;
-    const int pair = blockIdx.y;
     const PairState st = a.state[pair];
     if (!a.ignore_status && st.status != PAIR_ACTIVE) return;
 
@@ -407,7 +423,7 @@ __global__ void __launch_bounds__(OBJ_THREADS, 4) accumulate_kernel(const ObjArg
     if (begin >= end) {
         // empty source cloud (or empty shard slice): nothing to gather - the pipeline below would read the record
         // before `begin`.  The pair's partial rows are zero.
-        if (threadIdx.x < NRED) a.partial[((size_t)pair * a.blocks_per_pair + blockIdx.x) * NRED + threadIdx.x] = 0.0;
+        if (threadIdx.x < NRED) a.partial[((size_t)pair * a.blocks_per_pair + bx) * NRED + threadIdx.x] = 0.0;
         return;
     }
     AccT acc[NQ];
@@ -419,7 +435,7 @@ __global__ void __launch_bounds__(OBJ_THREADS, 4) accumulate_kernel(const ObjArg
     // software pipeline over the thread's points: while point `it` is being processed, the gather of
     // point it+1 (target record + covariance, addressed by its match) and the match index of point it+2
     // are already in flight - the kernel is bound by dependent-load latency otherwise
-    const int s_first = begin + blockIdx.x * a.ppt * OBJ_THREADS + threadIdx.x;
+    const int s_first = begin + bx * a.ppt * OBJ_THREADS + threadIdx.x;
     auto load_match = [&](int it) {
         const int s = s_first + it * OBJ_THREADS;
         return (it < a.ppt && s < end) ? a.match[s] : -1;
@@ -594,8 +610,13 @@ __global__ void __launch_bounds__(OBJ_THREADS, 4) accumulate_kernel(const ObjArg
 #pragma unroll
             for (int w = 0; w < OBJ_THREADS / 32; ++w) r += s_red[w][threadIdx.x];
         }
-        a.partial[((size_t)pair * a.blocks_per_pair + blockIdx.x) * NRED + threadIdx.x] = r;
+        a.partial[((size_t)pair * a.blocks_per_pair + bx) * NRED + threadIdx.x] = r;
     }
+}
+
+template <int D, typename Real>
+__global__ void __launch_bounds__(OBJ_THREADS, 4) accumulate_kernel(const ObjArgs<Real> a) {
+    accumulate_block<D, Real>(a, blockIdx.y, blockIdx.x);
 }
 
 }  // namespace gicp

@@ -250,37 +250,17 @@ __global__ void presum_kernel(const double* __restrict__ partial, int blocks_per
     out[((size_t)pair * out_per_pair + blockIdx.x) * NRED + threadIdx.x] = (s0 + s1) + (s2 + s3);
 }
 
+// Tail of one outer iteration of one pair, run by ONE thread: `sums` is the pair's summed reduced form
+// ([NRED] doubles, shared memory), `st` the pair's state (read by the caller).
 template <int D>
-__global__ void __launch_bounds__(SOLVE_WARPS * 32) solve_kernel(const SolveArgs a) {
+__device__ void solve_pair(const SolveArgs& a, const int pair, PairState st, const double* sums) {
     using DD = Dim<D>;
-    constexpr int NRED = DD::NRED, NQ = DD::NQ, NP = DD::NP;
-    __shared__ double s_red[SOLVE_WARPS][NRED];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pair = blockIdx.x * SOLVE_WARPS + warp;
-    if (pair >= a.n_pairs) return;
-    PairState st = a.state[pair];
-    if (!a.sum_out && st.status != PAIR_ACTIVE) return;
-    for (int j = lane; j < NRED; j += 32) {
-        double s = 0.0;
-        const double* p = a.partial + (size_t)pair * a.blocks_per_pair * NRED + j;
-        for (int b = 0; b < a.blocks_per_pair; ++b) s += p[(size_t)b * NRED];
-        s_red[warp][j] = s;
-    }
-    __syncwarp();
-    if (a.sum_out) {
-        for (int j = lane; j < NRED; j += 32) {
-            double v = s_red[warp][j];
-            if (j >= NQ + 2 && j < NQ + 2 + D) v = st.mu[j - NQ - 2];
-            a.sum_out[(size_t)pair * NRED + j] = v;
-        }
-        return;
-    }
-    if (lane != 0) return;
+    constexpr int NQ = DD::NQ;
     Reduced<D> red;
-    red.Hq = s_red[warp];
-    red.G = s_red[warp] + DD::NH;
-    red.c = s_red[warp][NQ];
-    const int inliers = (int)(s_red[warp][NQ + 1] + 0.5);
+    red.Hq = sums;
+    red.G = sums + DD::NH;
+    red.c = sums[NQ];
+    const int inliers = (int)(sums[NQ + 1] + 0.5);
     double dR[D][D], dtc[D], dtheta, fmin;
     inner_solve<D>(red, a.inner_max_iterations, dR, dtc, &dtheta, &fmin);
 
@@ -334,8 +314,36 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) solve_kernel(const SolveArgs
     write_T<D>(a.d_T + (size_t)pair * (D + 1) * (D + 1), st);
     a.d_converged[pair] = st.converged_at;
     a.state[pair] = st;
-    if (st.status != PAIR_ACTIVE) atomicSub(a.n_active, 1);
-    (void)NP;
+    if (st.status != PAIR_ACTIVE && a.n_active) atomicSub(a.n_active, 1);
+}
+
+template <int D>
+__global__ void __launch_bounds__(SOLVE_WARPS * 32) solve_kernel(const SolveArgs a) {
+    using DD = Dim<D>;
+    constexpr int NRED = DD::NRED, NQ = DD::NQ;
+    __shared__ double s_red[SOLVE_WARPS][NRED];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = blockIdx.x * SOLVE_WARPS + warp;
+    if (pair >= a.n_pairs) return;
+    PairState st = a.state[pair];
+    if (!a.sum_out && st.status != PAIR_ACTIVE) return;
+    for (int j = lane; j < NRED; j += 32) {
+        double s = 0.0;
+        const double* p = a.partial + (size_t)pair * a.blocks_per_pair * NRED + j;
+        for (int b = 0; b < a.blocks_per_pair; ++b) s += p[(size_t)b * NRED];
+        s_red[warp][j] = s;
+    }
+    __syncwarp();
+    if (a.sum_out) {
+        for (int j = lane; j < NRED; j += 32) {
+            double v = s_red[warp][j];
+            if (j >= NQ + 2 && j < NQ + 2 + D) v = st.mu[j - NQ - 2];
+            a.sum_out[(size_t)pair * NRED + j] = v;
+        }
+        return;
+    }
+    if (lane != 0) return;
+    solve_pair<D>(a, pair, st, s_red[warp]);
 }
 
 // initialise the per-pair state (gicp.py:107-110): T = T0 or identity, last_loss = inf
