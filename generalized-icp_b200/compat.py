@@ -56,21 +56,13 @@ def gicp_extended(source_points, target_points, max_iterations=100, tolerance=1e
                    max_distance_nearest_neighbors=float(max_distance_nearest_neighbors),
                    lambda_tangent=float(lambda_tangent), lambda_normal=float(lambda_normal),
                    covariance_model=int(covariance_model), **engine_params)
-    np_dtype = np.float64 if storage == "f64" else np.float32
-    s_dev = torch.as_tensor(np.ascontiguousarray(src[:, :dim], dtype=np_dtype), device=eng.device)
-    t_dev = torch.as_tensor(np.ascontiguousarray(tgt[:, :dim], dtype=np_dtype), device=eng.device)
-    eng.set_target(t_dev)                                   # gicp.py:104
-    eng.set_source(s_dev)                                   # gicp.py:111
-    res = eng.register(history=True)                        # gicp.py:116-167
-    n_outer = int(res.n_outer[0].item())
-    conv = int(res.converged_at[0].item())
+    r = eng.register_pair_host(src[:, :dim], tgt[:, :dim])  # gicp.py:104, 111, 116-167 in one staged round trip
+    n_outer, conv = r["n_outer"], r["converged_at"]
     n_T = n_outer if conv >= 0 else n_outer + 1             # appendix A rule 12
-    T_hist = res.T_hist[0, :n_T].cpu().numpy()
+    T_hist = r["T_hist"][:n_T]
     out = dict(T=T_hist[-1].copy(), all_T=[T_hist[i].copy() for i in range(n_T)], n_outer=n_outer,
-               converged_at=conv, loss_hist=res.loss_hist[0, :n_outer].cpu().numpy(),
-               inliers=res.inliers[0, :n_outer].cpu().numpy(), dim=dim)
-    out["tgt_cov"] = eng.covariances(1).cpu().numpy()
-    out["src_cov0"] = eng.covariances(0).cpu().numpy()
+               converged_at=conv, loss_hist=r["loss_hist"].copy(), inliers=r["inliers"].copy(), dim=dim,
+               tgt_cov=r["tgt_cov"], src_cov0=r["src_cov0"])
     if full_history:
         covs = eng.source_covariances_at(T_hist[:n_outer].reshape(n_outer, 1, dim + 1, dim + 1)).cpu().numpy()
         out["all_src_cov"] = [covs[i] for i in range(n_outer)]

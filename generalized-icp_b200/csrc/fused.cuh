@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(OBJ_THREADS) register_loop_kernel(const ObjArg
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NRED = Dim<D>::NRED;
     __shared__ double s_sum[NRED];
+    __shared__ SolveScratch<D> s_sc;
     const int pair = blockIdx.x;
     WarpStage<Real> ws = obj_warp_stage<Real>(smem_raw);   // one mbarrier per warp for the whole loop
     for (int it = 0; it < sa.max_iterations; ++it) {
@@ -24,7 +25,7 @@ __global__ void __launch_bounds__(OBJ_THREADS) register_loop_kernel(const ObjArg
         __syncthreads();
         if (threadIdx.x < NRED) s_sum[threadIdx.x] = oa.partial[(size_t)pair * NRED + threadIdx.x];
         __syncthreads();
-        if (threadIdx.x == 0) solve_pair<D>(sa, pair, sa.state[pair], s_sum);
+        if (threadIdx.x < 32) solve_pair<D>(sa, pair, sa.state[pair], s_sum, s_sc);   // warp 0, all lanes
         __syncthreads();                                   // the new state (global) is visible to the block
         if (sa.state[pair].status != PAIR_ACTIVE) break;
     }

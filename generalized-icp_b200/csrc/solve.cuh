@@ -43,6 +43,28 @@ template <int D> struct Reduced {
     }
 };
 
+// entry e of the dense form Hd[c * NP + a][d * NP + b] = H(a, b, c, d) of the packed reduced Hessian Hq [NAB][NS]
+// (K3b's layout): the solver applies H 5-8 times per LM iteration, as dense matrix-vector products
+template <int D> __device__ __forceinline__ double dense_H_entry(const double* Hq, int e) {
+    using DD = Dim<D>;
+    constexpr int DN = D * DD::NP;
+    const int row = e / DN, col = e % DN;
+    const int c_ = row / DD::NP, a = row % DD::NP, d = col / DD::NP, b = col % DD::NP;
+    return Hq[symidx(DD::NP, a, b) * DD::NS + symidx(D, c_, d)];
+}
+
+// shared-memory scratch of one warp's solve
+template <int D> struct SolveScratch {
+    static constexpr int NP = D + 1, DN = D * NP, NPAR = Dim<D>::NPAR;
+    double Hd[DN * DN];
+    double Z[DN], Zn[DN], Gam[DN];
+    double dZ[NPAR][DN], HdZ[NPAR][DN];
+    double A[NPAR][NPAR], g[NPAR];
+    double dR[D][D], dt[D];
+    double f, lam, dtheta;
+    int go;
+};
+
 template <int N> __device__ inline bool cholesky_solve(double A[N][N], double b[N]) {
     // in-place LL^T; returns false when A is not positive definite
     for (int j = 0; j < N; ++j) {
@@ -103,7 +125,9 @@ __device__ inline void compose_rotation(const double* step_rot, const double dR[
     }
 }
 
-// Minimise the reduced form.  On return dR, dt (centred frame) and the minimum value.
+// Minimise the reduced form, ONE-LANE version (packed Hessian).  Used in 2-D, where the 3-parameter problem is so
+// small that the shared-memory hand-overs of the warp-cooperative version below cost more than they save (measured:
+// fused 2-D registration 179 vs 205 us).  On return dR, dt (centred frame) and the minimum value.
 template <int D>
 __device__ void inner_solve(const Reduced<D>& red, int max_it, double dR[D][D], double dt[D], double* dtheta,
                             double* fmin) {
@@ -200,6 +224,137 @@ __device__ void inner_solve(const Reduced<D>& red, int max_it, double dR[D][D], 
     *fmin = f;
 }
 
+// Minimise the reduced form  f(Z) = c - 2<G,Z> + <Z, H Z>,  Z = [dt | dR - I]  (flat index c * NP + a), over
+// (dt, dR in SO(D)) by Levenberg-Marquardt.  WARP-COOPERATIVE: all 32 lanes of one warp call this with the same
+// arguments; the matrix-vector products, tangents and normal equations are spread over the lanes (one row or one
+// entry per lane, every sum in a fixed order), lane 0 runs the damped solve and the acceptance test.  A one-lane
+// version of the same algorithm executed ~17 k instructions per LM iteration in 3-D (it was the slowest kernel of a
+// small registration: 37 us per launch); this one executes ~1.3 k.  Results in sc.dR, sc.dt, sc.dtheta, sc.f.
+template <int D>
+__device__ void inner_solve_warp(SolveScratch<D>& sc, const double* G, double c0, int max_it, int lane) {
+    using SS = SolveScratch<D>;
+    constexpr int NP = SS::NP, DN = SS::DN, NPAR = SS::NPAR;
+    if (lane == 0) {
+        for (int i = 0; i < D; ++i) {
+            sc.dt[i] = 0.0;
+            for (int j = 0; j < D; ++j) sc.dR[i][j] = (i == j) ? 1.0 : 0.0;
+        }
+        sc.dtheta = 0.0;
+        sc.f = c0;
+        sc.lam = 1e-9;
+    }
+    if (lane < DN) sc.Z[lane] = 0.0;
+    __syncwarp();
+    for (int it = 0; it < max_it; ++it) {
+        // gradient wrt Z: Gam = 2 (H Z - G)
+        if (lane < DN) {
+            const double* row = sc.Hd + lane * DN;
+            double s = 0.0;
+            for (int e = 0; e < DN; ++e) s += row[e] * sc.Z[e];
+            sc.Gam[lane] = 2.0 * (s - G[lane]);
+        }
+        // tangent directions dZ_x: translations, then rotations [0 | E_k dR]
+        for (int q = lane; q < NPAR * DN; q += 32) {
+            const int x = q / DN, e = q % DN, c_ = e / NP, a = e % NP;
+            double v = 0.0;
+            if (x < D) {
+                v = (c_ == x && a == 0) ? 1.0 : 0.0;
+            } else if (a > 0) {
+                if constexpr (D == 2) {
+                    // E = [[0,-1],[1,0]]
+                    v = (c_ == 0) ? -sc.dR[1][a - 1] : sc.dR[0][a - 1];
+                } else {
+                    const int k = x - 3, k1 = (k + 1) % 3, k2 = (k + 2) % 3;  // (E_k M)[k1] = -M[k2], (E_k M)[k2] = M[k1]
+                    if (c_ == k1) v = -sc.dR[k2][a - 1];
+                    else if (c_ == k2) v = sc.dR[k1][a - 1];
+                }
+            }
+            sc.dZ[x][e] = v;
+        }
+        __syncwarp();
+        for (int q = lane; q < NPAR * DN; q += 32) {
+            const int x = q / DN, r = q % DN;
+            const double* row = sc.Hd + r * DN;
+            double s = 0.0;
+            for (int e = 0; e < DN; ++e) s += row[e] * sc.dZ[x][e];
+            sc.HdZ[x][r] = s;
+        }
+        __syncwarp();
+        if (lane < NPAR) {
+            double s = 0.0;
+            for (int e = 0; e < DN; ++e) s += sc.Gam[e] * sc.dZ[lane][e];
+            sc.g[lane] = s;
+        }
+        for (int q = lane; q < NPAR * NPAR; q += 32) {
+            const int x = q / NPAR, y = q % NPAR;
+            if (y <= x) {
+                double s = 0.0;
+                for (int e = 0; e < DN; ++e) s += sc.dZ[x][e] * sc.HdZ[y][e];
+                sc.A[x][y] = sc.A[y][x] = 2.0 * s;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            double f = sc.f, lam = sc.lam;
+            double gmax = 0.0;
+            for (int x = 0; x < NPAR; ++x) gmax = fmax(gmax, fabs(sc.g[x]));
+            bool go = gmax > 1e-11 * fmax(1.0, fabs(f));
+            if (go) {
+                bool accepted = false;
+                double stepmax = 0.0;
+                for (int tries = 0; tries < 40; ++tries) {
+                    double L[NPAR][NPAR], step[NPAR];
+                    for (int x = 0; x < NPAR; ++x) {
+                        for (int y = 0; y < NPAR; ++y) L[x][y] = sc.A[x][y];
+                        L[x][x] += lam * sc.A[x][x];
+                        step[x] = -sc.g[x];
+                    }
+                    if (!cholesky_solve<NPAR>(L, step)) { lam = fmax(lam * 10.0, 1e-6); continue; }
+                    double dRn[D][D], dtn[D], thn;
+                    compose_rotation<D>(step + D, sc.dR, sc.dtheta, dRn, &thn);
+                    for (int c_ = 0; c_ < D; ++c_) {
+                        dtn[c_] = sc.dt[c_] + step[c_];
+                        sc.Zn[c_ * NP] = dtn[c_];
+                        for (int j = 0; j < D; ++j) sc.Zn[c_ * NP + 1 + j] = dRn[c_][j] - (c_ == j ? 1.0 : 0.0);
+                    }
+                    // f(Zn) = c - 2 <G, Zn> + <Zn, H Zn>
+                    double lin = 0.0, quad = 0.0;
+                    for (int r = 0; r < DN; ++r) {
+                        const double* row = sc.Hd + r * DN;
+                        double hz = 0.0;
+                        for (int e = 0; e < DN; ++e) hz += row[e] * sc.Zn[e];
+                        lin += G[r] * sc.Zn[r];
+                        quad += sc.Zn[r] * hz;
+                    }
+                    const double fn = c0 - 2.0 * lin + quad;
+                    double pred = 0.0;
+                    for (int x = 0; x < NPAR; ++x) pred -= sc.g[x] * step[x];
+                    if (fn <= f || pred <= 1e-11 * fabs(f)) {
+                        for (int c_ = 0; c_ < D; ++c_) {
+                            sc.dt[c_] = dtn[c_];
+                            for (int j = 0; j < D; ++j) sc.dR[c_][j] = dRn[c_][j];
+                        }
+                        for (int e = 0; e < DN; ++e) sc.Z[e] = sc.Zn[e];
+                        sc.dtheta = thn;
+                        f = fn;
+                        lam = fmax(lam * 0.1, 1e-12);
+                        accepted = true;
+                        for (int x = 0; x < NPAR; ++x) stepmax = fmax(stepmax, fabs(step[x]));
+                        break;
+                    }
+                    lam = fmax(lam * 10.0, 1e-9);
+                }
+                if (!accepted || stepmax < 1e-14) go = false;
+            }
+            sc.f = f;
+            sc.lam = lam;
+            sc.go = go ? 1 : 0;
+        }
+        __syncwarp();
+        if (!sc.go) break;
+    }
+}
+
 struct SolveArgs {
     const double* partial;  // [n_pairs][blocks_per_pair][NRED]
     int blocks_per_pair;
@@ -250,19 +405,34 @@ __global__ void presum_kernel(const double* __restrict__ partial, int blocks_per
     out[((size_t)pair * out_per_pair + blockIdx.x) * NRED + threadIdx.x] = (s0 + s1) + (s2 + s3);
 }
 
-// Tail of one outer iteration of one pair, run by ONE thread: `sums` is the pair's summed reduced form
-// ([NRED] doubles, shared memory), `st` the pair's state (read by the caller).
+// Tail of one outer iteration of one pair, run by ONE WARP (all 32 lanes call it): `sums` is the pair's summed reduced
+// form ([NRED] doubles, shared memory), `sc` the warp's scratch, `st` the pair's state (read by the caller).
 template <int D>
-__device__ void solve_pair(const SolveArgs& a, const int pair, PairState st, const double* sums) {
+__device__ void solve_pair(const SolveArgs& a, const int pair, PairState st, const double* sums, SolveScratch<D>& sc) {
     using DD = Dim<D>;
-    constexpr int NQ = DD::NQ;
-    Reduced<D> red;
-    red.Hq = sums;
-    red.G = sums + DD::NH;
-    red.c = sums[NQ];
-    const int inliers = (int)(sums[NQ + 1] + 0.5);
+    constexpr int NQ = DD::NQ, DN2 = SolveScratch<D>::DN * SolveScratch<D>::DN;
+    const int lane = threadIdx.x & 31;
     double dR[D][D], dtc[D], dtheta, fmin;
-    inner_solve<D>(red, a.inner_max_iterations, dR, dtc, &dtheta, &fmin);
+    if constexpr (D == 2) {
+        if (lane != 0) return;
+        Reduced<D> red;
+        red.Hq = sums;
+        red.G = sums + DD::NH;
+        red.c = sums[NQ];
+        inner_solve<D>(red, a.inner_max_iterations, dR, dtc, &dtheta, &fmin);
+    } else {
+        for (int e = lane; e < DN2; e += 32) sc.Hd[e] = dense_H_entry<D>(sums, e);
+        __syncwarp();
+        inner_solve_warp<D>(sc, sums + DD::NH, sums[NQ], a.inner_max_iterations, lane);
+        if (lane != 0) return;
+        for (int i = 0; i < D; ++i) {
+            dtc[i] = sc.dt[i];
+            for (int j = 0; j < D; ++j) dR[i][j] = sc.dR[i][j];
+        }
+        dtheta = sc.dtheta;
+        fmin = sc.f;
+    }
+    const int inliers = (int)(sums[NQ + 1] + 0.5);
 
     const int it = st.iter;
     const double delta = fabs(st.last_loss - fmin);  // gicp.py:155
@@ -322,6 +492,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) solve_kernel(const SolveArgs
     using DD = Dim<D>;
     constexpr int NRED = DD::NRED, NQ = DD::NQ;
     __shared__ double s_red[SOLVE_WARPS][NRED];
+    __shared__ SolveScratch<D> s_sc[SOLVE_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pair = blockIdx.x * SOLVE_WARPS + warp;
     if (pair >= a.n_pairs) return;
@@ -342,8 +513,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) solve_kernel(const SolveArgs
         }
         return;
     }
-    if (lane != 0) return;
-    solve_pair<D>(a, pair, st, s_red[warp]);
+    solve_pair<D>(a, pair, st, s_red[warp], s_sc[warp]);
 }
 
 // initialise the per-pair state (gicp.py:107-110): T = T0 or identity, last_loss = inf
