@@ -572,7 +572,11 @@ int objective_args(gicpContext* h, ObjArgs<Real>& a, int& blocks_per_pair, bool 
     // enough blocks to fill the machine, as many points per thread as that allows (<= OBJ_MAX_PPT)
     const long long total_pts = (long long)std::max(span, 1) * S.n_clouds;
     int ppt = (int)(total_pts / (148LL * 8 * OBJ_THREADS));
-    ppt = std::max(1, std::min(OBJ_MAX_PPT, ppt));
+    // the accumulation's software pipeline has a fill bubble per thread (match index -> gathered record): longer
+    // per-thread runs amortise it when the batch is large enough.  Measured per 1024 pairs of the bench workload:
+    // 16 / 32 / 64 points per thread -> 9.66 / 9.16 / 9.31 ms (GICP_ACC_PPT: A/B timing)
+    const int ppt_cap = (getenv("GICP_ACC_PPT") && atoi(getenv("GICP_ACC_PPT")) > 0) ? atoi(getenv("GICP_ACC_PPT")) : 2 * OBJ_MAX_PPT;
+    ppt = std::max(1, std::min(ppt_cap, ppt));
     a.ppt = ppt;
     blocks_per_pair = std::max(1, (span + OBJ_THREADS * ppt - 1) / (OBJ_THREADS * ppt));
     a.blocks_per_pair = blocks_per_pair;
@@ -669,6 +673,7 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
     ObjArgs<Real> oc = oa;
     {
         int split = getenv("GICP_CORR_SPLIT") ? atoi(getenv("GICP_CORR_SPLIT")) : 2;
+        while (oa.ppt / split > OBJ_MAX_PPT / 2) split *= 2;   // the search keeps blocks of <= 8 points per thread
         while (split > 1 && oa.ppt % split) --split;
         oc.ppt = oa.ppt / std::max(split, 1);
     }

@@ -28,8 +28,9 @@ total = sum(v[1] for v in agg.values())
 with open(os.path.join(out_dir, f"launches_{tag}.md"), "w") as f:
     f.write(f"# ncu launch list ({tag}): `bench.py --pairs 512 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e`\n\n"
             "`ncu --metrics gpu__time_duration.sum --clock-control none` - per-launch times are cold-cache and\n"
-            "serialised: read the SHARES, not the absolutes.  All launches of the process (4 warm-up + 1 timed + 1\n"
-            "profiled step, plus the torch kernels that generate the synthetic clouds).\n\n"
+            "serialised: read the SHARES, not the absolutes.  All launches of the library's kernels and of CUB (4 warm-up\n"
+            "+ 1 timed + 1 profiled step; `--kernel-name regex:` keeps the torch kernels that generate the synthetic\n"
+            "clouds out of the list).\n\n"
             "| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f"| `{k}` | {v[0]} | {v[1]:.2f} | {100 * v[1] / total:.1f}% |\n")
