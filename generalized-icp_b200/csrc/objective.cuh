@@ -614,8 +614,10 @@ __device__ __forceinline__ void accumulate_block(const ObjArgs<Real>& a, const i
     }
 }
 
+// f32 storage: 128 registers, 4 blocks per SM.  f64 storage carries 72 fp64 accumulators per thread: 2 blocks per SM
+// and 255 registers instead of ~1.2 KB of spills per thread under the 128-register cap
 template <int D, typename Real>
-__global__ void __launch_bounds__(OBJ_THREADS, 4) accumulate_kernel(const ObjArgs<Real> a) {
+__global__ void __launch_bounds__(OBJ_THREADS, (sizeof(Real) == 8 && D == 3) ? 2 : 4) accumulate_kernel(const ObjArgs<Real> a) {
     accumulate_block<D, Real>(a, blockIdx.y, blockIdx.x);
 }
 

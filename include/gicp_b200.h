@@ -97,7 +97,9 @@ int gicpPromoteTargetToSource(gicpHandle h);
  *  d_loss_hist optional (n_clouds, max_iterations) f64: min_loss per outer iteration (gicp.py:154)
  *  d_T_hist    optional (n_clouds, max_iterations+1, dim+1, dim+1) f64: all_transformations (gicp.py:108,167)
  *  d_inliers   optional (n_clouds, max_iterations) i32: correspondences that passed the gate per iteration
- * Asynchronous on `stream` except for a 4-byte progress poll.                             */
+ * Asynchronous on `stream`: large pairs are driven by a host loop that runs a few iterations ahead of 4-byte
+ * progress polls (it returns once every pair has stopped); when every source cloud has <= 2048 points the whole
+ * loop is ONE kernel (fused.cuh) and the call returns immediately - synchronise `stream` before reading the outputs. */
 int gicpRegister(gicpHandle h, const double* h_T0, double* d_T, int32_t* d_n_outer, int32_t* d_converged,
                  double* d_loss_hist, double* d_T_hist, int32_t* d_inliers, void* stream);
 
