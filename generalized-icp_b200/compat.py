@@ -24,8 +24,8 @@ def apply_transformation(cloud, T):
     return np.dot(cloud[:, :d], T[:d, :d].T) + T[:d, d]
 
 
-def _engine(dim, storage):
-    key = (os.getpid(), dim, storage)
+def _engine(dim, storage, tag="main"):
+    key = (os.getpid(), dim, storage, tag)
     eng = _ENGINES.get(key)
     if eng is None:
         from .engine import GicpEngine
@@ -69,10 +69,33 @@ def gicp_extended(source_points, target_points, max_iterations=100, tolerance=1e
         hw_s, hw_t = [], []
         src64 = np.asarray(src[:, :dim], dtype=np.float64)
         tgt64 = np.asarray(tgt[:, :dim], dtype=np.float64)
-        for it in range(n_T - 1):                           # gicp.py:170-172, visualisation only
-            idx, _, W = eng.correspond(T_hist[it])
-            idx = idx.cpu().numpy()
-            W = W.cpu().numpy()
+        reps = n_T - 1
+        per_it = []
+        if 0 < reps and reps * max(len(src64), len(tgt64)) <= (1 << 22) and os.environ.get("GICP_COMPAT_BATCH_HISTORY", "1") != "0":
+            # gicp.py:170-172 (visualisation only): the correspondences and weights of EVERY outer iteration in one
+            # batched call - the pair replicated once per iteration on a second handle, T_k as the k-th pair's
+            # transform - instead of one host round trip per iteration (a batch equals its pairs bit for bit)
+            np_dt = np.float64 if storage == "f64" else np.float32
+            eh = _engine(dim, storage, "history")
+            eh.set_params(k=k, max_iterations=int(max_iterations), tolerance=float(tolerance),
+                          max_distance_correspondence=float(max_distance_correspondence),
+                          max_distance_nearest_neighbors=float(max_distance_nearest_neighbors),
+                          lambda_tangent=float(lambda_tangent), lambda_normal=float(lambda_normal),
+                          covariance_model=int(covariance_model), **engine_params)
+            n_s, n_t = len(src64), len(tgt64)
+            eh.set_target(torch.as_tensor(np.tile(np.ascontiguousarray(tgt[:, :dim], dtype=np_dt), (reps, 1)), device=eh.device),
+                          np.arange(reps + 1, dtype=np.int64) * n_t)
+            eh.set_source(torch.as_tensor(np.tile(np.ascontiguousarray(src[:, :dim], dtype=np_dt), (reps, 1)), device=eh.device),
+                          np.arange(reps + 1, dtype=np.int64) * n_s)
+            idx_all, _, W_all = eh.correspond(T_hist[:reps])
+            idx_all = idx_all.cpu().numpy().reshape(reps, n_s)
+            W_all = W_all.cpu().numpy().reshape(reps, n_s, dim, dim)
+            per_it = [(idx_all[it], W_all[it]) for it in range(reps)]
+        else:
+            for it in range(reps):                          # very large clouds: one call per iteration
+                idx, _, W = eng.correspond(T_hist[it])
+                per_it.append((idx.cpu().numpy(), W.cpu().numpy()))
+        for it, (idx, W) in enumerate(per_it):
             order = np.argsort(np.linalg.det(W))[-5:]
             q = np.zeros_like(src64)
             m = idx >= 0

@@ -56,6 +56,22 @@ if "2" in which and rank == 0:
                           "ms_per_pair": 1e3 * dt / len(pairs), "pairs_per_sec": len(pairs) / dt,
                           "mean_outer_iterations": float(np.mean(its))}))
 
+if "2" in which and rank == 0:
+    # the call the robot demo makes (robot-visualization.py:157-162): the full 7-tuple with every iteration's
+    # covariances and highest-weight correspondences
+    import gicp as shim
+    import contextlib
+    import io
+    scans, _ = demo_inputs.lidar_sequence(seed=1, num_rays=360, n_scans=30)
+    pairs = [([tuple(p) for p in scans[i]], [tuple(p) for p in scans[i + 1]]) for i in range(len(scans) - 1)]
+
+    def run7():
+        with contextlib.redirect_stdout(io.StringIO()):
+            return [len(shim.gicp(a, b, max_distance_nearest_neighbors=200, tolerance=1)[1]) for a, b in pairs]
+    dt, _ = timed(run7, 3)
+    print(json.dumps({"config": 2, "what": "robot scan sequence, 360 rays: gicp() with the reference's full 7-tuple (lists of tuples in)",
+                      "ms_per_pair": 1e3 * dt / len(pairs)}))
+
 if "3" in which and rank == 0:
     src, tgt, T = synthetic.patches3d_pair(**synthetic.CONFIG3, seed=0)
     eng = GicpEngine(3, "f32")

@@ -17,7 +17,8 @@ rays = int(sys.argv[1]) if len(sys.argv) > 1 else 360
 scans, _ = demo_inputs.lidar_sequence(seed=1, num_rays=rays, n_scans=30)
 pairs = [(np.asarray(scans[i], dtype=np.float64), np.asarray(scans[i + 1], dtype=np.float64)) for i in range(len(scans) - 1)]
 eng = GicpEngine(2, "f64")
-eng.set_params(k=6, max_distance_nearest_neighbors=200.0, max_distance_correspondence=150.0, tolerance=1.0)
+eng.set_params(k=6, max_distance_nearest_neighbors=200.0, max_distance_correspondence=150.0, tolerance=1.0,
+               inner_max_iterations=int(os.environ.get("INNER_MAX", 50)))
 dev = eng.device
 acc = {}
 

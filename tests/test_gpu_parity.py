@@ -220,6 +220,10 @@ def test_compat_tuple_and_print(golden, torch_cuda, capsys):
     assert np.array_equal(all_T[0], np.eye(3)) and np.array_equal(T, all_T[-1])
     assert c0.shape == (len(src), 2, 2) and ct.shape == (len(tgt), 2, 2)
     assert np.array_equal(allc[0], c0)
+    # gicp.py:170-172: the five highest-weight correspondences of the first iteration (T = I: independent of the
+    # inner solver), recorded from the reference; every iteration's set comes out of ONE batched call
+    assert len(hs) == len(ht) == len(all_T) - 1
+    assert np.abs(hs[0] - g["hw_src_0"]).max() < 1e-9 and np.abs(ht[0] - g["hw_tgt_0"]).max() < 1e-9
     assert "Converged at iteration" in capsys.readouterr().out
     import pickle
     pickle.loads(pickle.dumps(out))
