@@ -389,6 +389,17 @@ int launch_knn(gicpContext* h, CloudSet& cs, int* d_idx, double* d_dist, cudaStr
                                 (int)smem_g));                                                               \
         knn_general_kernel<D, Real, KC><<<GRID, KNN_THREADS, smem_g, st>>>(a, FROM_LIST);                    \
     } while (0)
+    if (latency_mode && cs.max_n <= KNN_BRUTE_MAX && slice_b < 0 &&
+        !(getenv("GICP_KNN_BRUTE") && atoi(getenv("GICP_KNN_BRUTE")) == 0)) {
+        // tiny clouds: brute force from shared memory, one block per cloud, one launch
+        const size_t smem_b = (size_t)cs.max_n * sizeof(PRec<Real>);
+        if (a.k <= 6) knn_brute_kernel<D, Real, 6><<<cs.n_clouds, KNN_BRUTE_THREADS, smem_b, st>>>(a);
+        else if (a.k <= 20) knn_brute_kernel<D, Real, 20><<<cs.n_clouds, KNN_BRUTE_THREADS, smem_b, st>>>(a);
+        else knn_brute_kernel<D, Real, 32><<<cs.n_clouds, KNN_BRUTE_THREADS, smem_b, st>>>(a);
+        h->launches += 1;
+        CU(cudaGetLastError());
+        return 0;
+    }
     if (fast) {
         CU(cudaMemsetAsync(h->ovf_count.p, 0, sizeof(int), st));
         CU(cudaFuncSetAttribute(knn_hist_kernel<D, Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));

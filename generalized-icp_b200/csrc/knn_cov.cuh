@@ -598,6 +598,100 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_lane_kernel(const KnnArgs<Rea
     knn_rank_and_finish<D, Real>(a, m, base + lane, my_idx, mx, my, mz, lk, li, lane, mcount, edge_lo);
 }
 
+// Sorted top-k (slots [KCAP-k, KCAP) live, INT_MAX = empty) -> radius test, optional index / distance outputs,
+// sample covariance about the mean (ddof = 1) and its regularised form, written for sorted position s_pos.
+template <int D, typename Real, int KCAP>
+__device__ __forceinline__ void topk_finish(const KnnArgs<Real>& a, const CloudMeta& m, int s_pos, int my_idx,
+                                            double (&ad)[KCAP], int (&ai)[KCAP]) {
+    // ---- covariance of the surviving neighbours (gicp.py:25-34, 5-17) ----
+    const size_t cloud_row0 = (size_t)m.pt_begin;
+    int cnt = 0;
+    double mean[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int s = 0; s < KCAP; ++s) {
+        const bool ok = (s >= KCAP - a.k) && ai[s] != INT_MAX && sqrt(ad[s]) < a.radius;
+        if (!ok && s >= KCAP - a.k) ai[s] = INT_MAX;
+        if (ok) {
+            ++cnt;
+            const Real* q = a.raw + (cloud_row0 + ai[s]) * D;
+#pragma unroll
+            for (int c = 0; c < D; ++c) mean[c] += (double)q[c];
+        }
+    }
+    if (a.knn_idx) {
+        int o = 0;
+        int* out = a.knn_idx + (cloud_row0 + my_idx) * (size_t)a.k;
+        double* outd = a.knn_dist ? a.knn_dist + (cloud_row0 + my_idx) * (size_t)a.k : nullptr;
+#pragma unroll
+        for (int s = 0; s < KCAP; ++s) {
+            if (s >= KCAP - a.k && ai[s] != INT_MAX) {
+                out[o] = ai[s];
+                if (outd) outd[o] = sqrt(ad[s]);
+                ++o;
+            }
+        }
+        for (; o < a.k; ++o) {
+            out[o] = -1;
+            if (outd) outd[o] = INFINITY;
+        }
+    }
+    constexpr int NS = Dim<D>::NS;
+    double C[NS];
+    bool ident = cnt <= 1;
+    if (!ident) {
+        const double inv = 1.0 / cnt;
+#pragma unroll
+        for (int c = 0; c < D; ++c) mean[c] *= inv;
+        double S[6] = {0, 0, 0, 0, 0, 0};  // 00 01 02 11 12 22
+#pragma unroll
+        for (int s = 0; s < KCAP; ++s) {
+            if (s >= KCAP - a.k && ai[s] != INT_MAX) {
+                const Real* q = a.raw + (cloud_row0 + ai[s]) * D;
+                const double d0 = (double)q[0] - mean[0], d1 = (double)q[1] - mean[1];
+                const double d2 = (D == 3) ? (double)q[D - 1] - mean[2] : 0.0;
+                S[0] += d0 * d0; S[1] += d0 * d1; S[2] += d0 * d2;
+                S[3] += d1 * d1; S[4] += d1 * d2; S[5] += d2 * d2;
+            }
+        }
+        const double f = 1.0 / (cnt - 1);  // ddof = 1 (np.cov default, gicp.py:12)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) S[i] *= f;
+        bool finite = true;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) finite = finite && isfinite(S[i]);
+        if (!finite) {
+            ident = true;  // gicp.py:31-32
+        } else if constexpr (D == 2) {
+            // eigenvector of the largest eigenvalue (gicp.py:14-16): C = lam_n I + (lam_t-lam_n) v v^T
+            const double phi = 0.5 * atan2(2.0 * S[1], S[0] - S[3]);
+            double sn, cs;
+            sincos(phi, &sn, &cs);
+            const double dl = a.lam_t - a.lam_n;
+            C[0] = a.lam_n + dl * cs * cs;
+            C[1] = dl * cs * sn;
+            C[2] = a.lam_n + dl * sn * sn;
+        } else {
+            // normal = eigenvector of the smallest eigenvalue: C = lam_t I - (lam_t-lam_n) n n^T
+            double n[3];
+            smallest_eigvec3(S[0], S[1], S[2], S[3], S[4], S[5], n);
+            const double dl = a.lam_t - a.lam_n;
+            C[0] = a.lam_t - dl * n[0] * n[0];
+            C[1] = -dl * n[0] * n[1];
+            C[2] = -dl * n[0] * n[2];
+            C[3] = a.lam_t - dl * n[1] * n[1];
+            C[4] = -dl * n[1] * n[2];
+            C[5] = a.lam_t - dl * n[2] * n[2];
+        }
+    }
+    if (ident) {
+        if constexpr (D == 2) { C[0] = 1.0; C[1] = 0.0; C[2] = 1.0; }
+        else { C[0] = 1.0; C[1] = 0.0; C[2] = 0.0; C[3] = 1.0; C[4] = 0.0; C[5] = 1.0; }
+    }
+    Real* out = a.cov_sorted + (size_t)s_pos * NS;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) out[i] = (Real)C[i];
+}
+
 // ================================================================================================
 // general path
 // ================================================================================================
@@ -700,93 +794,7 @@ __device__ __forceinline__ void knn_general_chunk(const KnnArgs<Real>& a, int cl
     }
 
     if (!valid) return;
-    // ---- covariance of the surviving neighbours (gicp.py:25-34, 5-17) ----
-    const size_t cloud_row0 = (size_t)m.pt_begin;
-    int cnt = 0;
-    double mean[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-    for (int s = 0; s < KCAP; ++s) {
-        const bool ok = (s >= KCAP - a.k) && ai[s] != INT_MAX && sqrt(ad[s]) < a.radius;
-        if (!ok && s >= KCAP - a.k) ai[s] = INT_MAX;
-        if (ok) {
-            ++cnt;
-            const Real* q = a.raw + (cloud_row0 + ai[s]) * D;
-#pragma unroll
-            for (int c = 0; c < D; ++c) mean[c] += (double)q[c];
-        }
-    }
-    if (a.knn_idx) {
-        int o = 0;
-        int* out = a.knn_idx + (cloud_row0 + my_idx) * (size_t)a.k;
-        double* outd = a.knn_dist ? a.knn_dist + (cloud_row0 + my_idx) * (size_t)a.k : nullptr;
-#pragma unroll
-        for (int s = 0; s < KCAP; ++s) {
-            if (s >= KCAP - a.k && ai[s] != INT_MAX) {
-                out[o] = ai[s];
-                if (outd) outd[o] = sqrt(ad[s]);
-                ++o;
-            }
-        }
-        for (; o < a.k; ++o) {
-            out[o] = -1;
-            if (outd) outd[o] = INFINITY;
-        }
-    }
-    constexpr int NS = Dim<D>::NS;
-    double C[NS];
-    bool ident = cnt <= 1;
-    if (!ident) {
-        const double inv = 1.0 / cnt;
-#pragma unroll
-        for (int c = 0; c < D; ++c) mean[c] *= inv;
-        double S[6] = {0, 0, 0, 0, 0, 0};  // 00 01 02 11 12 22
-#pragma unroll
-        for (int s = 0; s < KCAP; ++s) {
-            if (s >= KCAP - a.k && ai[s] != INT_MAX) {
-                const Real* q = a.raw + (cloud_row0 + ai[s]) * D;
-                const double d0 = (double)q[0] - mean[0], d1 = (double)q[1] - mean[1];
-                const double d2 = (D == 3) ? (double)q[D - 1] - mean[2] : 0.0;
-                S[0] += d0 * d0; S[1] += d0 * d1; S[2] += d0 * d2;
-                S[3] += d1 * d1; S[4] += d1 * d2; S[5] += d2 * d2;
-            }
-        }
-        const double f = 1.0 / (cnt - 1);  // ddof = 1 (np.cov default, gicp.py:12)
-#pragma unroll
-        for (int i = 0; i < 6; ++i) S[i] *= f;
-        bool finite = true;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) finite = finite && isfinite(S[i]);
-        if (!finite) {
-            ident = true;  // gicp.py:31-32
-        } else if constexpr (D == 2) {
-            // eigenvector of the largest eigenvalue (gicp.py:14-16): C = lam_n I + (lam_t-lam_n) v v^T
-            const double phi = 0.5 * atan2(2.0 * S[1], S[0] - S[3]);
-            double sn, cs;
-            sincos(phi, &sn, &cs);
-            const double dl = a.lam_t - a.lam_n;
-            C[0] = a.lam_n + dl * cs * cs;
-            C[1] = dl * cs * sn;
-            C[2] = a.lam_n + dl * sn * sn;
-        } else {
-            // normal = eigenvector of the smallest eigenvalue: C = lam_t I - (lam_t-lam_n) n n^T
-            double n[3];
-            smallest_eigvec3(S[0], S[1], S[2], S[3], S[4], S[5], n);
-            const double dl = a.lam_t - a.lam_n;
-            C[0] = a.lam_t - dl * n[0] * n[0];
-            C[1] = -dl * n[0] * n[1];
-            C[2] = -dl * n[0] * n[2];
-            C[3] = a.lam_t - dl * n[1] * n[1];
-            C[4] = -dl * n[1] * n[2];
-            C[5] = a.lam_t - dl * n[2] * n[2];
-        }
-    }
-    if (ident) {
-        if constexpr (D == 2) { C[0] = 1.0; C[1] = 0.0; C[2] = 1.0; }
-        else { C[0] = 1.0; C[1] = 0.0; C[2] = 0.0; C[3] = 1.0; C[4] = 0.0; C[5] = 1.0; }
-    }
-    Real* out = a.cov_sorted + (size_t)(base + lane) * NS;
-#pragma unroll
-    for (int i = 0; i < NS; ++i) out[i] = (Real)C[i];
+    topk_finish<D, Real, KCAP>(a, m, base + lane, my_idx, ad, ai);
 }
 
 // from_list = 0: grid (blocks, n_clouds), one warp per 32 sorted points.
@@ -822,6 +830,55 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_general_kernel(const KnnArgs<
             knn_general_chunk<D, Real, KCAP>(a, it.x, it.y, end, wbase, ws, lane);
             __syncwarp();
         }
+    }
+}
+
+// ================================================================================================
+// brute force for small clouds (latency path): one thread per query, every point of the cloud streamed
+// from shared memory (a broadcast read), exact float64 keys, sorted top-k in registers.  Measured per cloud
+// (grid build + k-NN, stream synchronised): 48-point scans 77 -> 60 us, 192-360-point scans 95 -> 102 us - n serial
+// fp64 candidate tests per thread overtake the grid walk's ~20 TMA round trips at ~150 points, hence the cap.
+// grid (n_clouds), KNN_BRUTE_THREADS threads; dynamic shared memory n_max * sizeof(PRec<Real>).
+// ================================================================================================
+constexpr int KNN_BRUTE_MAX = 128;
+constexpr int KNN_BRUTE_THREADS = 128;
+
+template <int D, typename Real, int KCAP>
+__global__ void __launch_bounds__(KNN_BRUTE_THREADS) knn_brute_kernel(const KnnArgs<Real> a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    PRec<Real>* pts = reinterpret_cast<PRec<Real>*>(smem_raw);
+    const CloudMeta m = a.meta[blockIdx.x];
+    const int n = m.pt_end - m.pt_begin;
+    for (int i = threadIdx.x; i < n; i += KNN_BRUTE_THREADS) pts[i] = a.spts[m.pt_begin + i];
+    __syncthreads();
+    const double r2cap = a.radius * a.radius * (1.0 + 1e-12);
+    for (int q = threadIdx.x; q < n; q += KNN_BRUTE_THREADS) {
+        const PRec<Real> me = pts[q];
+        double ad[KCAP];
+        int ai[KCAP];
+#pragma unroll
+        for (int s = 0; s < KCAP; ++s) {
+            const bool live = s >= KCAP - a.k;
+            ad[s] = live ? r2cap : -1.0;
+            ai[s] = live ? INT_MAX : -1;
+        }
+        for (int j = 0; j < n; ++j) {
+            const PRec<Real> c = pts[j];
+            const double e2 = exact_d2((double)c.x - (double)me.x, (double)c.y - (double)me.y, (double)c.z - (double)me.z);
+            const int ci = (int)c.idx;
+            bool lt_s = key_less(e2, ci, ad[KCAP - 1], ai[KCAP - 1]);
+            if (lt_s) {
+#pragma unroll
+                for (int s = KCAP - 1; s > 0; --s) {
+                    const bool lt_prev = key_less(e2, ci, ad[s - 1], ai[s - 1]);
+                    if (lt_prev) { ad[s] = ad[s - 1]; ai[s] = ai[s - 1]; }
+                    else if (lt_s) { ad[s] = e2; ai[s] = ci; }
+                    lt_s = lt_prev;
+                }
+                if (lt_s) { ad[0] = e2; ai[0] = ci; }
+            }
+        }
+        topk_finish<D, Real, KCAP>(a, m, m.pt_begin + q, (int)me.idx, ad, ai);
     }
 }
 

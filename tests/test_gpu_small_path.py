@@ -11,7 +11,7 @@ import demo_inputs
 from conftest import golden_names
 
 pytestmark = pytest.mark.gpu
-SWITCHES = ("GICP_SMALL_GRID", "GICP_FUSED_LOOP")
+SWITCHES = ("GICP_SMALL_GRID", "GICP_FUSED_LOOP", "GICP_KNN_BRUTE")
 
 
 @pytest.fixture()
