@@ -326,7 +326,7 @@ def run_b200(args):
                "h2d_bytes_per_step": int(h_src.numel() * 4 + h_tgt.numel() * 4) * world,
                "d2h_bytes_per_step": int(my_pairs * (16 * 8 + 4 + 4)) * world,
                "pairs_per_sec": pairs_all * args.steps / float(dt.item()),
-               "api": "GicpEngine.register_host_batch (chunks doubling from 1/8 of a chunk up to <= 1024 pairs; set_target/set_source/register over ctypes -> "
+               "api": "GicpEngine.register_host_batch (chunks of <= 1024 pairs, first chunk 1/8; set_target/set_source/register over ctypes -> "
                       "libgicp_b200.so), pinned host buffers, H2D of the next chunk overlapped with compute"}
         del h_src, h_tgt
 
