@@ -214,7 +214,6 @@ int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, cudaStrea
     CU(g.meta.ensure((size_t)nc * sizeof(CloudMeta)));
     CU(g.bbox.ensure((size_t)nc * 6 * sizeof(double)));
     CU(g.cell_start.ensure((size_t)(g.total_cells + 1) * sizeof(int)));
-    CU(h->cell_count.ensure((size_t)(g.total_cells + 1) * sizeof(int)));
     CU(g.spts.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(PRec<Real>)));
     CU(g.inv_perm.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(int)));
     CU(h->keys.ensure((size_t)std::max<int64_t>(n, 1) * 4));
@@ -244,20 +243,21 @@ int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, cudaStrea
                                                           g.meta.as<CloudMeta>(), g.bbox.as<double>());
     CU(g.lut.ensure((size_t)nc * 3 * GICP_LUT_N * sizeof(int)));
     morton_lut_kernel<<<dim3(3 * GICP_LUT_N / 256, nc), 256, 0, st>>>(g.meta.as<CloudMeta>(), g.lut.as<int>());
-    CU(cudaMemsetAsync(h->cell_count.p, 0, (size_t)(g.total_cells + 1) * sizeof(int), st));
+    // the cell histogram is built in the table itself and scanned in place (no second 4-byte-per-cell buffer)
+    CU(cudaMemsetAsync(g.cell_start.p, 0, (size_t)(g.total_cells + 1) * sizeof(int), st));
     h->launches += 3;
     if (n > 0) {
         const int bx = (cs.max_n + 255) / 256;
         cell_key_kernel<D, Real><<<dim3(bx, nc), 256, 0, st>>>(pts, g.meta.as<CloudMeta>(), h->keys.as<unsigned>(),
-                                                               h->vals.as<int>(), h->cell_count.as<int>());
+                                                               h->vals.as<int>(), g.cell_start.as<int>());
         h->launches += 1;
     }
     {   // cell_start = exclusive scan of the histogram
         size_t tmp = 0;
-        CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, h->cell_count.as<int>(), g.cell_start.as<int>(),
+        CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, g.cell_start.as<int>(), g.cell_start.as<int>(),
                                          (int)(g.total_cells + 1), st));
         CU(h->cub_tmp.ensure(tmp));
-        CU(cub::DeviceScan::ExclusiveSum(h->cub_tmp.p, tmp, h->cell_count.as<int>(), g.cell_start.as<int>(),
+        CU(cub::DeviceScan::ExclusiveSum(h->cub_tmp.p, tmp, g.cell_start.as<int>(), g.cell_start.as<int>(),
                                          (int)(g.total_cells + 1), st));
         h->launches += 2;
     }
