@@ -135,7 +135,7 @@ struct gicpContext {
     gicpParams prm;
     CloudSet src, tgt;
     DevBuf keys, keys_alt, vals, vals_alt, cub_tmp, cell_count, bbox_part;
-    DevBuf state, partial, partial2, red, T_dev, n_active, prev_match, slack, ovf_count, ovf_list;
+    DevBuf state, partial, partial2, red, T_dev, n_active, prev_match, slack, ovf_count, ovf_list, active_list;
     static constexpr int NPOLL = 8;
     int* h_poll = nullptr;  // pinned [NPOLL]: progress polls in flight
     cudaEvent_t poll_ev[NPOLL] = {};
@@ -574,6 +574,8 @@ int objective_args(gicpContext* h, ObjArgs<Real>& a, int& blocks_per_pair, bool 
     a.track_max_cells = getenv("GICP_TRACK_CELLS") ? atoi(getenv("GICP_TRACK_CELLS")) : 1 << 30;
     a.centre_first = getenv("GICP_CENTRE_FIRST") ? atoi(getenv("GICP_CENTRE_FIRST")) : 1;
     a.shell_search = getenv("GICP_SHELL_SEARCH") ? atoi(getenv("GICP_SHELL_SEARCH")) : 1;
+    a.active_list = nullptr;
+    a.n_list = nullptr;
     int span = S.max_n;
     if (allow_slice && h->comm && S.n_clouds == 1) {
         a.slice_begin = (int)(S.n_total * h->rank / h->n_ranks);
@@ -653,6 +655,8 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
     sa.d_T_hist = d_T_hist;
     sa.d_inliers = d_inliers;
     sa.n_active = h->n_active.as<int>();
+    sa.active_list = nullptr;
+    sa.n_list = nullptr;
     // Small pairs (every source cloud fits one block): the whole outer loop in one launch (fused.cuh).  Not with a
     // communicator (the all-reduce sits between the stages) and not while per-stage timing is on.
     const bool sharded_pair = h->comm && np == 1;
@@ -699,6 +703,20 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
     // mode keeps a blocking poll on a fixed schedule (all ranks see the same count: they solve bit-identical forms).
     constexpr int LOOK = 3;
     int issued = 0, checked = 0;
+    // Large batches: after every iteration the still-active pairs are compacted into a list (one small block), and
+    // the next launches cover only `known_active` slots of it - the latest polled count, an upper bound of the list's
+    // length since the count only falls.  Without it every launch of the convergence tail starts tens of thousands
+    // of blocks that return at once (4096 pairs: 131 k blocks per search launch).
+    const bool use_list = !sharded && np >= 64 && !(getenv("GICP_ACTIVE_LIST") && atoi(getenv("GICP_ACTIVE_LIST")) == 0);
+    int known_active = np;
+    if (use_list) {
+        CU(h->active_list.ensure((size_t)(np + 1) * sizeof(int)));
+        int* lst = h->active_list.as<int>();
+        compact_active_kernel<<<1, COMPACT_THREADS, 0, st>>>(h->state.as<PairState>(), np, lst + 1, lst);
+        h->launches += 1;
+        oa.active_list = oc.active_list = sa.active_list = lst + 1;
+        oa.n_list = oc.n_list = sa.n_list = lst;
+    }
     for (int it = 0; it < h->prm.max_iterations; ++it) {
         bool done = false;
         while (checked < issued && !done) {
@@ -708,16 +726,18 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
             if (q == cudaErrorNotReady) { cudaGetLastError(); break; }
             CU(q);
             done = h->h_poll[slot] <= 0;
+            known_active = std::min(known_active, std::max(h->h_poll[slot], 1));
             ++checked;
         }
         if (done) break;
+        const int gy = use_list ? known_active : np;
         {
             ProfScope prof(h, GICP_STAGE_CORRESPOND, st);
-            correspond_kernel<D, Real><<<cgrid, OBJ_THREADS, obj_smem(oc.ppt), st>>>(oc);
+            correspond_kernel<D, Real><<<dim3(cgrid.x, gy), OBJ_THREADS, obj_smem(oc.ppt), st>>>(oc);
         }
         {
             ProfScope prof(h, GICP_STAGE_ACCUMULATE, st);
-            accumulate_kernel<D, Real><<<ogrid, OBJ_THREADS, 0, st>>>(oa);
+            accumulate_kernel<D, Real><<<dim3(ogrid.x, gy), OBJ_THREADS, 0, st>>>(oa);
         }
         {
             ProfScope prof(h, GICP_STAGE_SOLVE, st);
@@ -738,8 +758,13 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
                 solve_kernel<D><<<sgrid, SOLVE_WARPS * 32, 0, st>>>(s2);
                 h->launches += 4;
             } else {
-                solve_kernel<D><<<sgrid, SOLVE_WARPS * 32, 0, st>>>(sa);
+                solve_kernel<D><<<use_list ? (gy + SOLVE_WARPS - 1) / SOLVE_WARPS : sgrid, SOLVE_WARPS * 32, 0, st>>>(sa);
                 h->launches += 3;
+                if (use_list) {
+                    int* lst = h->active_list.as<int>();
+                    compact_active_kernel<<<1, COMPACT_THREADS, 0, st>>>(h->state.as<PairState>(), np, lst + 1, lst);
+                    h->launches += 1;
+                }
             }
         }
         if (!sharded || (it + 1) % 2 == 0) {
@@ -897,7 +922,7 @@ int gicpDestroy(gicpHandle h) {
     h->src.release();
     h->tgt.release();
     DevBuf* bufs[] = {&h->keys, &h->keys_alt, &h->vals, &h->vals_alt, &h->cub_tmp, &h->cell_count, &h->bbox_part,
-                      &h->state, &h->partial, &h->partial2, &h->red, &h->T_dev, &h->n_active, &h->prev_match, &h->slack, &h->ovf_count, &h->ovf_list};
+                      &h->state, &h->partial, &h->partial2, &h->red, &h->T_dev, &h->n_active, &h->prev_match, &h->slack, &h->ovf_count, &h->ovf_list, &h->active_list};
     for (DevBuf* b : bufs) b->release();
     if (h->h_poll) cudaFreeHost(h->h_poll);
     for (cudaEvent_t e : h->poll_ev) if (e) cudaEventDestroy(e);

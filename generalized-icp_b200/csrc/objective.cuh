@@ -56,7 +56,18 @@ template <typename Real> struct ObjArgs {
     int track_max_cells;      // per-lane walk only when the ball spans at most this many cells
     int centre_first;
     int shell_search;         // untracked lanes search per-lane shells before the cooperative phase
+    // optional compacted list of the pairs that are still iterating (compact_active_kernel): blockIdx.y is then a
+    // slot of that list, and slots beyond *n_list return at once - in the convergence tail of a large batch a launch
+    // otherwise starts (and immediately retires) tens of thousands of blocks of finished pairs
+    const int* active_list;
+    const int* n_list;
 };
+
+template <typename Real>
+__device__ __forceinline__ int obj_pair_of_block(const ObjArgs<Real>& a) {
+    if (!a.active_list) return (int)blockIdx.y;
+    return ((int)blockIdx.y < *a.n_list) ? a.active_list[blockIdx.y] : -1;
+}
 
 // One block of the search: points [bx * ppt * OBJ_THREADS, ...) of pair `pair`.  `ws` is the warp's TMA stage
 // (buffer, mbarrier, phase); it is carried by the caller so that the fused registration loop (register_loop_kernel)
@@ -384,8 +395,10 @@ __device__ __forceinline__ WarpStage<Real> obj_warp_stage(unsigned char* smem_ra
 template <int D, typename Real>
 __global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<Real> a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int pair = obj_pair_of_block(a);
+    if (pair < 0) return;
     WarpStage<Real> ws = obj_warp_stage<Real>(smem_raw);
-    correspond_block<D, Real>(a, blockIdx.y, blockIdx.x, ws, smem_raw);
+    correspond_block<D, Real>(a, pair, blockIdx.x, ws, smem_raw);
 }
 
 // One block of the accumulation: points [bx * ppt * OBJ_THREADS, ...) of pair `pair` -> partial[pair][bx][NRED]
@@ -618,7 +631,9 @@ __device__ __forceinline__ void accumulate_block(const ObjArgs<Real>& a, const i
 // and 255 registers instead of ~1.2 KB of spills per thread under the 128-register cap
 template <int D, typename Real>
 __global__ void __launch_bounds__(OBJ_THREADS, (sizeof(Real) == 8 && D == 3) ? 2 : 4) accumulate_kernel(const ObjArgs<Real> a) {
-    accumulate_block<D, Real>(a, blockIdx.y, blockIdx.x);
+    const int pair = obj_pair_of_block(a);
+    if (pair < 0) return;
+    accumulate_block<D, Real>(a, pair, blockIdx.x);
 }
 
 }  // namespace gicp

@@ -371,6 +371,8 @@ struct SolveArgs {
     double* d_T_hist;       // optional [n_pairs][max_iterations+1][(D+1)^2]
     int* d_inliers;         // optional [n_pairs][max_iterations]
     int* n_active;
+    const int* active_list;   // optional (see ObjArgs): warp w of the grid handles pair active_list[w]
+    const int* n_list;
 };
 
 template <int D> __device__ inline void write_T(double* out, const PairState& st) {
@@ -494,7 +496,11 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) solve_kernel(const SolveArgs
     __shared__ double s_red[SOLVE_WARPS][NRED];
     __shared__ SolveScratch<D> s_sc[SOLVE_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pair = blockIdx.x * SOLVE_WARPS + warp;
+    int pair = blockIdx.x * SOLVE_WARPS + warp;
+    if (a.active_list) {
+        if (pair >= *a.n_list) return;
+        pair = a.active_list[pair];
+    }
     if (pair >= a.n_pairs) return;
     PairState st = a.state[pair];
     if (!a.sum_out && st.status != PAIR_ACTIVE) return;
@@ -514,6 +520,35 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) solve_kernel(const SolveArgs
         return;
     }
     solve_pair<D>(a, pair, st, s_red[warp], s_sc[warp]);
+}
+
+// One block: the pairs that are still iterating, in ascending order -> list[0 .. *n_list)
+constexpr int COMPACT_THREADS = 1024;
+__global__ void __launch_bounds__(COMPACT_THREADS) compact_active_kernel(const PairState* __restrict__ state, int n_pairs,
+                                                                         int* __restrict__ list, int* __restrict__ n_list) {
+    __shared__ int s_warp[COMPACT_THREADS / 32];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int p0 = 0; p0 < n_pairs; p0 += COMPACT_THREADS) {
+        const int p = p0 + threadIdx.x;
+        const bool act = p < n_pairs && state[p].status == PAIR_ACTIVE;
+        const unsigned bal = __ballot_sync(0xffffffffu, act);
+        if (lane == 0) s_warp[w] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int i = 0; i < COMPACT_THREADS / 32; ++i) {
+            const int c = s_warp[i];
+            if (i < w) before += c;
+            total += c;
+        }
+        if (act) list[s_base + before + __popc(bal & ((1u << lane) - 1u))] = p;
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_list = s_base;
 }
 
 // initialise the per-pair state (gicp.py:107-110): T = T0 or identity, last_loss = inf
