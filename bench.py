@@ -301,9 +301,9 @@ def run_b200(args):
         h_tgt = torch.empty(tgt.shape, dtype=tgt.dtype, pin_memory=True)
         h_src.copy_(src)
         h_tgt.copy_(tgt)
-        # <= 1024 pairs per chunk and at least two full chunks, so that a small first chunk (1/8) exists whose
+        # <= 2048 pairs per chunk (measured: 512 / 1024 / 2048 -> 93.1 / 96.4 / 97.5 % of the device-resident rate) and at least two full chunks, so that a small first chunk (1/8) exists whose
         # upload is the only exposed one (register_host_batch)
-        chunk_pairs = max(1, min(int(os.environ.get("GICP_E2E_CHUNK", "1024")), (my_pairs + 1) // 2))
+        chunk_pairs = max(1, min(int(os.environ.get("GICP_E2E_CHUNK", "2048")), (my_pairs + 1) // 2))
 
         def e2e_step():
             # host buffers in, host results out; the H2D copy of chunk i+1 overlaps the registration of chunk i
@@ -326,7 +326,7 @@ def run_b200(args):
                "h2d_bytes_per_step": int(h_src.numel() * 4 + h_tgt.numel() * 4) * world,
                "d2h_bytes_per_step": int(my_pairs * (16 * 8 + 4 + 4)) * world,
                "pairs_per_sec": pairs_all * args.steps / float(dt.item()),
-               "api": "GicpEngine.register_host_batch (chunks of <= 1024 pairs, first chunk 1/8; set_target/set_source/register over ctypes -> "
+               "api": "GicpEngine.register_host_batch (chunks of <= 2048 pairs, first chunk 1/8; set_target/set_source/register over ctypes -> "
                       "libgicp_b200.so), pinned host buffers, H2D of the next chunk overlapped with compute"}
         del h_src, h_tgt
 
