@@ -392,8 +392,11 @@ __device__ __forceinline__ WarpStage<Real> obj_warp_stage(unsigned char* smem_ra
     return ws;
 }
 
+// Occupancy decides this kernel (divergent dependent loads): 3-D fp32 is compiled for 10 blocks per SM = 48 registers
+// (measured per 512 pairs: natural 64 registers 14.73 ms, 48 registers 13.83 ms, 40 registers 14.26 ms; 128
+// registers 21.6 ms).  The other instantiations keep 8 blocks per SM (64 registers, what the compiler chose unprompted).
 template <int D, typename Real>
-__global__ void __launch_bounds__(OBJ_THREADS) correspond_kernel(const ObjArgs<Real> a) {
+__global__ void __launch_bounds__(OBJ_THREADS, (D == 3 && sizeof(Real) == 4) ? 10 : 8) correspond_kernel(const ObjArgs<Real> a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int pair = obj_pair_of_block(a);
     if (pair < 0) return;
