@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("GICP_B200_LIB") or os.path.join(_HERE, "libgicp_b200.
 # every symbol include/gicp_b200.h declares
 SYMBOLS = [
     "gicpCreate", "gicpDestroy", "gicpGetLastError", "gicpVersion", "gicpDefaultParams", "gicpSetParams",
-    "gicpSetTarget", "gicpSetSource", "gicpPromoteTargetToSource", "gicpRegister", "gicpKnn", "gicpCovariances", "gicpCorrespond",
+    "gicpSetTarget", "gicpSetSource", "gicpSetPair", "gicpPromoteTargetToSource", "gicpRegister", "gicpKnn", "gicpCovariances", "gicpCorrespond",
     "gicpNormalEquations", "gicpSourceCovariancesAt", "gicpCommGetUniqueId", "gicpCommInit", "gicpCommDestroy",
     "gicpLaunchCount", "gicpProfile", "gicpProfileRead", "gicpRayCast",
 ]
@@ -54,6 +54,7 @@ def load():
     lib.gicpSetParams.argtypes = [vp, C.POINTER(GicpParams)]
     for f in (lib.gicpSetTarget, lib.gicpSetSource):
         f.argtypes = [vp, vp, C.POINTER(i64), i32, vp]
+    lib.gicpSetPair.argtypes = [vp, vp, C.POINTER(i64), vp, C.POINTER(i64), i32, vp]
     lib.gicpPromoteTargetToSource.argtypes = [vp]
     lib.gicpRegister.argtypes = [vp, dp, vp, vp, vp, vp, vp, vp, vp]
     lib.gicpKnn.argtypes = [vp, C.c_int, vp, vp, vp]

@@ -158,6 +158,9 @@ struct gicpContext {
     // sharded-source mode
     void* comm = nullptr;
     int n_ranks = 1, rank = 0;
+    // gicpSetPair: the source side of a small pair is set up on this stream while the target side runs on the caller's
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -927,6 +930,9 @@ int gicpDestroy(gicpHandle h) {
     if (h->h_poll) cudaFreeHost(h->h_poll);
     for (cudaEvent_t e : h->poll_ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
     delete h;
     return 0;
 }
@@ -956,6 +962,49 @@ int gicpSetSource(gicpHandle h, const void* d_points, const int64_t* h_offsets, 
     if (check(h)) return 1;
     if (!h_offsets) return fail("null offsets");
     return DISPATCH(h, set_cloud, h, GICP_SOURCE, d_points, h_offsets, n_clouds, (cudaStream_t)stream);
+}
+
+namespace {
+// true when set_cloud takes the latency path for these clouds (small_grid_kernel + one k-NN launch): that path
+// touches only the side's own buffers, none of the handle's shared scratch (same conditions as build_grid / launch_knn)
+bool latency_path(const gicpContext* h, const int64_t* off, int n_clouds) {
+    if (getenv("GICP_SMALL_GRID") && atoi(getenv("GICP_SMALL_GRID")) == 0) return false;
+    if (n_clouds <= 0 || off[0] != 0 || h->prm.max_cells_per_cloud > (1LL << 20)) return false;
+    int64_t max_n = 0;
+    for (int i = 1; i <= n_clouds; ++i) {
+        if (off[i] < off[i - 1]) return false;
+        max_n = std::max<int64_t>(max_n, off[i] - off[i - 1]);
+    }
+    return max_n <= SMALL_GRID_MAX && off[n_clouds] > 0 && off[n_clouds] <= 65536;
+}
+}  // namespace
+
+int gicpSetPair(gicpHandle h, const void* d_target, const int64_t* h_target_offsets, const void* d_source,
+                const int64_t* h_source_offsets, int32_t n_clouds, void* stream) {
+    if (check(h)) return 1;
+    if (!h_target_offsets || !h_source_offsets) return fail("null offsets");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool concurrent = !h->comm && !h->prof_on && latency_path(h, h_target_offsets, n_clouds) &&
+                            latency_path(h, h_source_offsets, n_clouds);
+    if (!concurrent) {
+        if (DISPATCH(h, set_cloud, h, GICP_TARGET, d_target, h_target_offsets, n_clouds, st)) return 1;
+        return DISPATCH(h, set_cloud, h, GICP_SOURCE, d_source, h_source_offsets, n_clouds, st);
+    }
+    if (!h->side_stream) {
+        CU(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    // fork: the side stream sees everything the caller queued on `stream` so far (the upload of the clouds);
+    // join: `stream` continues only after the source side is set up
+    CU(cudaEventRecord(h->ev_fork, st));
+    CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+    const int rc_t = DISPATCH(h, set_cloud, h, GICP_TARGET, d_target, h_target_offsets, n_clouds, st);
+    const int rc_s = rc_t ? 1 : DISPATCH(h, set_cloud, h, GICP_SOURCE, d_source, h_source_offsets, n_clouds, h->side_stream);
+    CU(cudaEventRecord(h->ev_join, h->side_stream));
+    CU(cudaStreamWaitEvent(st, h->ev_join, 0));
+    h->last_stream = st;
+    return rc_t || rc_s;
 }
 
 int gicpPromoteTargetToSource(gicpHandle h) {

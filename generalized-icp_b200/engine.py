@@ -102,6 +102,19 @@ class GicpEngine:
         """Grid build + covariances of the source(s): gicp.py:111."""
         self._set(SOURCE, points, offsets)
 
+    def set_pair(self, target, source, target_offsets=None, source_offsets=None):
+        """Both sides of one gicp() call (gicp.py:104 and :111) through gicpSetPair: same result as set_target +
+        set_source; the set-up kernels of small clouds run concurrently on the device."""
+        tp, toff = self._prep(target, target_offsets)
+        sp, soff = self._prep(source, source_offsets)
+        if len(toff) != len(soff):
+            raise ValueError("source and target need the same number of clouds")
+        self._keep[TARGET], self._keep[SOURCE] = tp, sp
+        self._n[TARGET], self._n[SOURCE] = (tp.shape[0], len(toff) - 1), (sp.shape[0], len(soff) - 1)
+        i64p = C.POINTER(C.c_int64)
+        _lib.check(self.lib.gicpSetPair(self._h, _ptr(tp), toff.ctypes.data_as(i64p), _ptr(sp), soff.ctypes.data_as(i64p),
+                                        len(toff) - 1, self._stream()))
+
     def promote_target_to_source(self):
         """Scan sequences: the current target (grids + covariances) becomes the source of the next pair
         (robot-visualization.py:250-251) without being rebuilt."""
@@ -154,8 +167,7 @@ class GicpEngine:
         hv[:n_s] = src
         hv[pad_s:rows] = tgt
         self._pp_dev[:rows].copy_(self._pp_host[:rows], non_blocking=True)
-        self.set_target(self._pp_dev[pad_s:rows])
-        self.set_source(self._pp_dev[:n_s])
+        self.set_pair(self._pp_dev[pad_s:rows], self._pp_dev[:n_s])
         # outputs: [T | loss_hist | T_hist | src_cov | tgt_cov] (f64, NaN-filled) and [n_outer | converged | inliers] (i32)
         sizes = [d1 * d1, mi, (mi + 1) * d1 * d1, n_s * d * d, n_t * d * d]
         offs = np.concatenate([[0], np.cumsum(sizes)])

@@ -125,3 +125,52 @@ def test_small_3d_f32_both_paths(both_paths):
     assert nf == nm and np.array_equal(kf, km)
     assert np.abs(cf - cm).max() < 2e-4
     assert np.abs(Tf - Tm).max() < 1e-5
+
+
+def test_set_pair_equals_separate_calls():
+    """gicpSetPair (both sides in one call; the two single-block set-ups run concurrently on the device) against
+    gicpSetTarget + gicpSetSource: bit-identical grids, covariances and registration, repeated so that a race between
+    the two internal streams would show; a large pair takes the sequential branch of the same call."""
+    import torch
+    from generalized_icp_b200 import synthetic
+    from generalized_icp_b200.engine import GicpEngine
+    scans, _ = demo_inputs.lidar_sequence(seed=5, num_rays=360, n_scans=5)
+    eng_a, eng_b = GicpEngine(2, "f64"), GicpEngine(2, "f64")
+    for e in (eng_a, eng_b):
+        e.set_params(k=6, max_distance_nearest_neighbors=200.0, tolerance=1.0)
+    for rep in range(3):
+        for i in range(4):
+            s = torch.as_tensor(np.asarray(scans[i]), dtype=torch.float64, device="cuda")
+            t = torch.as_tensor(np.asarray(scans[i + 1]), dtype=torch.float64, device="cuda")
+            eng_a.set_target(t)
+            eng_a.set_source(s)
+            ra = eng_a.register(history=True)
+            eng_b.set_pair(t, s)
+            rb = eng_b.register(history=True)
+            assert int(ra.n_outer[0]) == int(rb.n_outer[0])
+            assert torch.equal(ra.T, rb.T)
+            n = int(ra.n_outer[0])
+            assert torch.equal(ra.T_hist[0, :n], rb.T_hist[0, :n])
+            for side in (0, 1):
+                assert torch.equal(eng_a.covariances(side), eng_b.covariances(side))
+                assert torch.equal(eng_a.knn(side)[0], eng_b.knn(side)[0])
+    # a batch of small pairs with different sizes per side
+    offs_t = np.array([0, 300, 300 + 217, 300 + 217 + 360], dtype=np.int64)
+    offs_s = np.array([0, 280, 280 + 360, 280 + 360 + 90], dtype=np.int64)
+    rng = np.random.default_rng(0)
+    tb = torch.as_tensor(rng.uniform(0, 500, (int(offs_t[-1]), 2)), device="cuda")
+    sb = torch.as_tensor(rng.uniform(0, 500, (int(offs_s[-1]), 2)), device="cuda")
+    eng_a.set_target(tb, offs_t); eng_a.set_source(sb, offs_s)
+    eng_b.set_pair(tb, sb, offs_t, offs_s)
+    for side in (0, 1):
+        assert torch.equal(eng_a.covariances(side), eng_b.covariances(side))
+    assert torch.equal(eng_a.register(history=False).T, eng_b.register(history=False).T)
+    # large clouds: the same entry point, sequential branch
+    s3, t3, _ = synthetic.patches3d_pair(n=20000, n_patches=8, cube=40.0, patch=30.0, seed=4)
+    e3a, e3b = GicpEngine(3, "f32"), GicpEngine(3, "f32")
+    for e in (e3a, e3b):
+        e.set_params(k=20, max_distance_nearest_neighbors=5.0, max_distance_correspondence=2.0)
+    s3 = torch.as_tensor(s3, dtype=torch.float32, device="cuda"); t3 = torch.as_tensor(t3, dtype=torch.float32, device="cuda")
+    e3a.set_target(t3); e3a.set_source(s3)
+    e3b.set_pair(t3, s3)
+    assert torch.equal(e3a.register(history=False).T, e3b.register(history=False).T)
