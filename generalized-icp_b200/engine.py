@@ -168,27 +168,40 @@ class GicpEngine:
         hv[pad_s:rows] = tgt
         self._pp_dev[:rows].copy_(self._pp_host[:rows], non_blocking=True)
         self.set_pair(self._pp_dev[pad_s:rows], self._pp_dev[:n_s])
-        # outputs: [T | loss_hist | T_hist | src_cov | tgt_cov] (f64, NaN-filled) and [n_outer | converged | inliers] (i32)
+        # outputs: [T | loss_hist | T_hist | src_cov | tgt_cov] (f64) followed by [n_outer | converged | inliers] (i32)
+        # in ONE cached device buffer with a pinned host mirror: one device->host copy, no fill kernels (the rows the
+        # loop did not reach are set to NaN on the host copy)
         sizes = [d1 * d1, mi, (mi + 1) * d1 * d1, n_s * d * d, n_t * d * d]
-        offs = np.concatenate([[0], np.cumsum(sizes)])
-        dbuf = torch.full((int(offs[-1]),), float("nan"), dtype=torch.float64, device=self.device)
-        ibuf = torch.zeros((2 + mi,), dtype=torch.int32, device=self.device)
-        dp, ip = dbuf.data_ptr(), ibuf.data_ptr()
+        offs = [0]
+        for z in sizes:
+            offs.append(offs[-1] + z)
+        nd = offs[-1]
+        tot = nd + (2 + mi + 1) // 2
+        if getattr(self, "_po_len", -1) < tot:
+            cap = max(tot, 4096)
+            self._po_dev = torch.empty((cap,), dtype=torch.float64, device=self.device)
+            self._po_host = torch.empty((cap,), dtype=torch.float64, pin_memory=True)
+            self._po_len = cap
+        dp = self._po_dev.data_ptr()
+        ip = dp + 8 * nd
         vp = C.c_void_p
         st = self._stream()
-        _lib.check(self.lib.gicpRegister(self._h, None, vp(dp), vp(ip), vp(ip + 4), vp(dp + 8 * int(offs[1])),
-                                         vp(dp + 8 * int(offs[2])), vp(ip + 8), st))
+        _lib.check(self.lib.gicpRegister(self._h, None, vp(dp), vp(ip), vp(ip + 4), vp(dp + 8 * offs[1]),
+                                         vp(dp + 8 * offs[2]), vp(ip + 8), st))
         if n_s:
-            _lib.check(self.lib.gicpCovariances(self._h, SOURCE, vp(dp + 8 * int(offs[3])), st))
+            _lib.check(self.lib.gicpCovariances(self._h, SOURCE, vp(dp + 8 * offs[3]), st))
         if n_t:
-            _lib.check(self.lib.gicpCovariances(self._h, TARGET, vp(dp + 8 * int(offs[4])), st))
-        hd = dbuf.cpu().numpy()
-        hi = ibuf.cpu().numpy()
+            _lib.check(self.lib.gicpCovariances(self._h, TARGET, vp(dp + 8 * offs[4]), st))
+        self._po_host[:tot].copy_(self._po_dev[:tot], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        hd = self._po_host.numpy()[:tot].copy()     # the pinned mirror is reused by the next call
+        hi = hd[nd:].view(np.int32)
         n_outer, conv = int(hi[0]), int(hi[1])
-        return dict(T=hd[:offs[1]].reshape(d1, d1), loss_hist=hd[offs[1]:offs[2]][:n_outer],
-                    T_hist=hd[offs[2]:offs[3]].reshape(mi + 1, d1, d1), src_cov0=hd[offs[3]:offs[4]].reshape(n_s, d, d),
-                    tgt_cov=hd[offs[4]:offs[5]].reshape(n_t, d, d), n_outer=n_outer, converged_at=conv,
-                    inliers=hi[2:2 + mi][:n_outer])
+        T_hist = hd[offs[2]:offs[3]].reshape(mi + 1, d1, d1)
+        T_hist[(n_outer if conv >= 0 else n_outer + 1):] = np.nan   # rows the loop wrote: SURVEY appendix A rule 12
+        return dict(T=hd[:offs[1]].reshape(d1, d1), loss_hist=hd[offs[1]:offs[2]][:n_outer], T_hist=T_hist,
+                    src_cov0=hd[offs[3]:offs[4]].reshape(n_s, d, d), tgt_cov=hd[offs[4]:offs[5]].reshape(n_t, d, d),
+                    n_outer=n_outer, converged_at=conv, inliers=hi[2:2 + mi][:n_outer])
 
     def register_host_batch(self, h_src, h_tgt, offsets, chunk_pairs=1024, history=False):
         """Batches that live in (pinned) HOST memory: pairs are registered in chunks, and the host->device
