@@ -12,37 +12,6 @@
 
 namespace gicp {
 
-template <int D> struct Reduced {
-    using DD = Dim<D>;
-    const double* Hq;  // [NAB][NS]
-    const double* G;   // [D][NP]
-    double c;
-    __device__ double H(int a, int b, int c_, int d) const {
-        return Hq[symidx(DD::NP, a, b) * DD::NS + symidx(D, c_, d)];
-    }
-    // out[c][a] = sum_{d,b} H(a,b,c,d) Z[d][b]
-    __device__ void apply(const double Z[D][D + 1], double out[D][D + 1]) const {
-        for (int c_ = 0; c_ < D; ++c_)
-            for (int a = 0; a < DD::NP; ++a) {
-                double s = 0.0;
-                for (int d = 0; d < D; ++d)
-                    for (int b = 0; b < DD::NP; ++b) s += H(a, b, c_, d) * Z[d][b];
-                out[c_][a] = s;
-            }
-    }
-    __device__ double eval(const double Z[D][D + 1]) const {
-        double HZ[D][D + 1];
-        apply(Z, HZ);
-        double lin = 0.0, quad = 0.0;
-        for (int c_ = 0; c_ < D; ++c_)
-            for (int a = 0; a < DD::NP; ++a) {
-                lin += G[c_ * DD::NP + a] * Z[c_][a];
-                quad += Z[c_][a] * HZ[c_][a];
-            }
-        return c - 2.0 * lin + quad;
-    }
-};
-
 // entry e of the dense form Hd[c * NP + a][d * NP + b] = H(a, b, c, d) of the packed reduced Hessian Hq [NAB][NS]
 // (K3b's layout): the solver applies H 5-8 times per LM iteration, as dense matrix-vector products
 template <int D> __device__ __forceinline__ double dense_H_entry(const double* Hq, int e) {
@@ -125,102 +94,83 @@ __device__ inline void compose_rotation(const double* step_rot, const double dR[
     }
 }
 
-// Minimise the reduced form, ONE-LANE version (packed Hessian).  Used in 2-D, where the 3-parameter problem is so
-// small that the shared-memory hand-overs of the warp-cooperative version below cost more than they save (measured:
-// fused 2-D registration 179 vs 205 us).  On return dR, dt (centred frame) and the minimum value.
-template <int D>
-__device__ void inner_solve(const Reduced<D>& red, int max_it, double dR[D][D], double dt[D], double* dtheta,
-                            double* fmin) {
-    using DD = Dim<D>;
-    constexpr int NP = DD::NP, NPAR = DD::NPAR, NROT = NPAR - D;
-    for (int i = 0; i < D; ++i) {
-        dt[i] = 0.0;
-        for (int j = 0; j < D; ++j) dR[i][j] = (i == j) ? 1.0 : 0.0;
-    }
-    *dtheta = 0.0;
-    double Z[D][D + 1];
-    for (int i = 0; i < D; ++i)
-        for (int a = 0; a < NP; ++a) Z[i][a] = 0.0;
-    double f = red.c;
+// 2-D, ONE LANE: Levenberg-Marquardt on the reduced form  f(Z) = c - 2<G,Z> + <Z, H Z>,  Z = [dt | dR - I]  (the same
+// iteration as the warp-cooperative 3-D version below: same damping, acceptance and stop rules), evaluated on the
+// projection of the form onto the four numbers Z depends on.  With dR = rot(th):
+//     Z = [[tx, p, -q], [ty, q, p]],  u = (tx, ty, p, q) = (tx, ty, cos th - 1, sin th),  Z_flat = B u,
+// so f = c - 2 (B^T G).u + u^T (B^T H B) u with a constant 6x4 matrix B of 0 / +-1 entries.  M = B^T H B (10 distinct
+// numbers) and B^T G are formed once; an LM iteration then costs ~150 register-resident flops.  (The first version
+// applied the packed 6x6 form five times per LM iteration with its index arithmetic: ~3 k instructions of one lane,
+// 2/3 of the time of a small registration - every other warp of the fused loop waits for this lane.  The
+// warp-cooperative formulation was measured slower than one lane in 2-D: its hand-overs cost more than 3 parameters
+// can save.)
+__device__ inline void inner_solve_2d(const double* Hq, const double* G, double c0, int max_it, double dR[2][2],
+                                      double dt[2], double* dtheta, double* fmin) {
+    auto Hd = [&](int e, int f) { return dense_H_entry<2>(Hq, e * 6 + f); };
+    const double M00 = Hd(0, 0), M01 = Hd(0, 3), M02 = Hd(0, 1) + Hd(0, 5), M03 = Hd(0, 4) - Hd(0, 2);
+    const double M11 = Hd(3, 3), M12 = Hd(3, 1) + Hd(3, 5), M13 = Hd(3, 4) - Hd(3, 2);
+    const double M22 = Hd(1, 1) + 2.0 * Hd(1, 5) + Hd(5, 5);
+    const double M23 = (Hd(1, 4) - Hd(1, 2)) + (Hd(5, 4) - Hd(5, 2));
+    const double M33 = Hd(4, 4) - 2.0 * Hd(4, 2) + Hd(2, 2);
+    const double b0 = G[0], b1 = G[3], b2 = G[1] + G[5], b3 = G[4] - G[2];
+    double tx = 0.0, ty = 0.0, th = 0.0, cs = 1.0, sn = 0.0;   // dR = rot(th) = [[cs, -sn], [sn, cs]]
+    double f = c0;
     double lam = 1e-9;
     for (int it = 0; it < max_it; ++it) {
-        // gradient wrt Z
-        double Gam[D][D + 1];
-        red.apply(Z, Gam);
-        for (int c = 0; c < D; ++c)
-            for (int a = 0; a < NP; ++a) Gam[c][a] = 2.0 * (Gam[c][a] - red.G[c * NP + a]);
-        // tangent directions dZ_x: translations, then rotations [0 | E_k dR]
-        double dZ[NPAR][D][D + 1];
-        for (int x = 0; x < NPAR; ++x)
-            for (int c = 0; c < D; ++c)
-                for (int a = 0; a < NP; ++a) dZ[x][c][a] = 0.0;
-        for (int c = 0; c < D; ++c) dZ[c][c][0] = 1.0;
-        if constexpr (D == 2) {
-            // E = [[0,-1],[1,0]]
-            for (int j = 0; j < 2; ++j) { dZ[2][0][1 + j] = -dR[1][j]; dZ[2][1][1 + j] = dR[0][j]; }
-        } else {
-            for (int k = 0; k < 3; ++k) {
-                const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;  // (E_k M)[k1] = -M[k2], (E_k M)[k2] = M[k1]
-                for (int j = 0; j < 3; ++j) { dZ[3 + k][k1][1 + j] = -dR[k2][j]; dZ[3 + k][k2][1 + j] = dR[k1][j]; }
-            }
-        }
-        double g[NPAR], A[NPAR][NPAR], HdZ[NPAR][D][D + 1];
-        for (int x = 0; x < NPAR; ++x) {
-            red.apply(dZ[x], HdZ[x]);
-            double s = 0.0;
-            for (int c = 0; c < D; ++c)
-                for (int a = 0; a < NP; ++a) s += Gam[c][a] * dZ[x][c][a];
-            g[x] = s;
-        }
-        double gmax = 0.0;
-        for (int x = 0; x < NPAR; ++x) {
-            gmax = fmax(gmax, fabs(g[x]));
-            for (int y = 0; y <= x; ++y) {
-                double s = 0.0;
-                for (int c = 0; c < D; ++c)
-                    for (int a = 0; a < NP; ++a) s += dZ[x][c][a] * HdZ[y][c][a];
-                A[x][y] = A[y][x] = 2.0 * s;
-            }
-        }
+        // gradient wrt u: r = 2 (M u - b);  tangents: d/dtx = e0, d/dty = e1, d/dth = (0, 0, -sin th, cos th)
+        const double p = cs - 1.0, q = sn;
+        const double r0 = 2.0 * (M00 * tx + M01 * ty + M02 * p + M03 * q - b0);
+        const double r1 = 2.0 * (M01 * tx + M11 * ty + M12 * p + M13 * q - b1);
+        const double r2 = 2.0 * (M02 * tx + M12 * ty + M22 * p + M23 * q - b2);
+        const double r3 = 2.0 * (M03 * tx + M13 * ty + M23 * p + M33 * q - b3);
+        const double w2 = -sn, w3 = cs;
+        const double g[3] = {r0, r1, r2 * w2 + r3 * w3};
+        double A[3][3];
+        A[0][0] = 2.0 * M00;
+        A[1][0] = A[0][1] = 2.0 * M01;
+        A[1][1] = 2.0 * M11;
+        A[2][0] = A[0][2] = 2.0 * (M02 * w2 + M03 * w3);
+        A[2][1] = A[1][2] = 2.0 * (M12 * w2 + M13 * w3);
+        A[2][2] = 2.0 * (w2 * (M22 * w2 + M23 * w3) + w3 * (M23 * w2 + M33 * w3));
+        const double gmax = fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2])));
         if (!(gmax > 1e-11 * fmax(1.0, fabs(f)))) break;
         bool accepted = false;
         double stepmax = 0.0;
         for (int tries = 0; tries < 40; ++tries) {
-            double L[NPAR][NPAR], step[NPAR];
-            for (int x = 0; x < NPAR; ++x) {
-                for (int y = 0; y < NPAR; ++y) L[x][y] = A[x][y];
+            double L[3][3], step[3];
+            for (int x = 0; x < 3; ++x) {
+                for (int y = 0; y < 3; ++y) L[x][y] = A[x][y];
                 L[x][x] += lam * A[x][x];
                 step[x] = -g[x];
             }
-            if (!cholesky_solve<NPAR>(L, step)) { lam = fmax(lam * 10.0, 1e-6); continue; }
-            double dRn[D][D], dtn[D], thn, Zn[D][D + 1];
-            compose_rotation<D>(step + D, dR, *dtheta, dRn, &thn);
-            for (int c = 0; c < D; ++c) {
-                dtn[c] = dt[c] + step[c];
-                Zn[c][0] = dtn[c];
-                for (int j = 0; j < D; ++j) Zn[c][1 + j] = dRn[c][j] - (c == j ? 1.0 : 0.0);
-            }
-            const double fn = red.eval(Zn);
-            double pred = 0.0;
-            for (int x = 0; x < NPAR; ++x) pred -= g[x] * step[x];
+            if (!cholesky_solve<3>(L, step)) { lam = fmax(lam * 10.0, 1e-6); continue; }
+            const double thn = th + step[2];
+            double sn_n, cs_n;
+            sincos(thn, &sn_n, &cs_n);
+            const double txn = tx + step[0], tyn = ty + step[1], pn = cs_n - 1.0, qn = sn_n;
+            const double m0 = M00 * txn + M01 * tyn + M02 * pn + M03 * qn;
+            const double m1 = M01 * txn + M11 * tyn + M12 * pn + M13 * qn;
+            const double m2 = M02 * txn + M12 * tyn + M22 * pn + M23 * qn;
+            const double m3 = M03 * txn + M13 * tyn + M23 * pn + M33 * qn;
+            const double lin = b0 * txn + b1 * tyn + b2 * pn + b3 * qn;
+            const double quad = txn * m0 + tyn * m1 + pn * m2 + qn * m3;
+            const double fn = c0 - 2.0 * lin + quad;
+            const double pred = -(g[0] * step[0] + g[1] * step[1] + g[2] * step[2]);
             if (fn <= f || pred <= 1e-11 * fabs(f)) {
-                for (int c = 0; c < D; ++c) {
-                    dt[c] = dtn[c];
-                    for (int j = 0; j < D; ++j) dR[c][j] = dRn[c][j];
-                    for (int a = 0; a < NP; ++a) Z[c][a] = Zn[c][a];
-                }
-                *dtheta = thn;
+                tx = txn; ty = tyn; th = thn; cs = cs_n; sn = sn_n;
                 f = fn;
                 lam = fmax(lam * 0.1, 1e-12);
                 accepted = true;
-                for (int x = 0; x < NPAR; ++x) stepmax = fmax(stepmax, fabs(step[x]));
+                stepmax = fmax(fabs(step[0]), fmax(fabs(step[1]), fabs(step[2])));
                 break;
             }
             lam = fmax(lam * 10.0, 1e-9);
         }
-        (void)NROT;
         if (!accepted || stepmax < 1e-14) break;
     }
+    dt[0] = tx; dt[1] = ty;
+    dR[0][0] = cs; dR[0][1] = -sn; dR[1][0] = sn; dR[1][1] = cs;
+    *dtheta = th;
     *fmin = f;
 }
 
@@ -417,11 +367,7 @@ __device__ void solve_pair(const SolveArgs& a, const int pair, PairState st, con
     double dR[D][D], dtc[D], dtheta, fmin;
     if constexpr (D == 2) {
         if (lane != 0) return;
-        Reduced<D> red;
-        red.Hq = sums;
-        red.G = sums + DD::NH;
-        red.c = sums[NQ];
-        inner_solve<D>(red, a.inner_max_iterations, dR, dtc, &dtheta, &fmin);
+        inner_solve_2d(sums, sums + DD::NH, sums[NQ], a.inner_max_iterations, dR, dtc, &dtheta, &fmin);
     } else {
         for (int e = lane; e < DN2; e += 32) sc.Hd[e] = dense_H_entry<D>(sums, e);
         __syncwarp();
