@@ -10,14 +10,28 @@
 
 namespace gicp {
 
+// `init_bbox` != nullptr: the kernel also initialises its pair (identity start, what init_state_kernel and the two
+// memsets of the match / slack arrays do on the multi-launch path) - a small registration is then ONE launch.
 template <int D, typename Real>
-__global__ void __launch_bounds__(OBJ_THREADS) register_loop_kernel(const ObjArgs<Real> oa, const SolveArgs sa) {
+__global__ void __launch_bounds__(OBJ_THREADS) register_loop_kernel(const ObjArgs<Real> oa, const SolveArgs sa,
+                                                                    const double* init_bbox) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NRED = Dim<D>::NRED;
     __shared__ double s_sum[NRED];
     __shared__ SolveScratch<D> s_sc;
     const int pair = blockIdx.x;
     WarpStage<Real> ws = obj_warp_stage<Real>(smem_raw);   // one mbarrier per warp for the whole loop
+    if (init_bbox) {
+        if (threadIdx.x == 0)
+            init_pair_state<D>(sa.state, nullptr, init_bbox, pair, sa.d_T, sa.d_T_hist,
+                               sa.max_iterations, sa.d_n_outer, sa.d_converged);
+        const CloudMeta ms = oa.src_meta[pair];
+        for (int s = ms.pt_begin + (int)threadIdx.x; s < ms.pt_end; s += OBJ_THREADS) {
+            oa.match[s] = -1;
+            if (oa.slack) oa.slack[s] = 0.f;
+        }
+        __syncthreads();
+    }
     for (int it = 0; it < sa.max_iterations; ++it) {
         correspond_block<D, Real>(oa, pair, 0, ws, smem_raw);
         __syncthreads();                                   // this block's matches are visible to the block

@@ -81,6 +81,7 @@ struct CloudSet {
     int64_t n_total = 0;
     int max_n = 0;
     DevBuf d_offsets;   // int32 [n_clouds+1]
+    int inline_n = -1;  // >= 0: one small cloud of that many points, its offsets travel as a kernel argument (no upload)
     Grid knn;           // grid of the covariance neighbourhoods (cell ~ knn radius / 4)
     Grid nn;            // grid of the correspondence search (cell ~ d_max / 2): the target is searched in it,
                         // the source is only ORDERED by it (compact warps in K3).  Built only when the k-NN
@@ -234,7 +235,7 @@ int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, cudaStrea
         small_grid_kernel<D, Real><<<nc, SMALL_GRID_THREADS, 0, st>>>(pts, offs, h_target, budget, g.meta.as<CloudMeta>(),
                                                                       g.bbox.as<double>(), g.lut.as<int>(),
                                                                       g.cell_start.as<int>(), g.spts.as<PRec<Real>>(),
-                                                                      g.inv_perm.as<int>(), 1);
+                                                                      g.inv_perm.as<int>(), 1, cs.inline_n);
         h->launches += 1;
         CU(cudaGetLastError());
         g.built = true;
@@ -453,6 +454,19 @@ double auto_nn_cell(const gicpContext* h) {
     return 0.5 * r;
 }
 
+// true when set_cloud takes the latency path for these clouds (small_grid_kernel + one k-NN launch): that path
+// touches only the side's own buffers, none of the handle's shared scratch (same conditions as build_grid / launch_knn)
+bool latency_path(const gicpContext* h, const int64_t* off, int n_clouds) {
+    if (getenv("GICP_SMALL_GRID") && atoi(getenv("GICP_SMALL_GRID")) == 0) return false;
+    if (n_clouds <= 0 || off[0] != 0 || h->prm.max_cells_per_cloud > (1LL << 20)) return false;
+    int64_t max_n = 0;
+    for (int i = 1; i <= n_clouds; ++i) {
+        if (off[i] < off[i - 1]) return false;
+        max_n = std::max<int64_t>(max_n, off[i] - off[i - 1]);
+    }
+    return max_n <= SMALL_GRID_MAX && off[n_clouds] > 0 && off[n_clouds] <= 65536;
+}
+
 template <int D, typename Real>
 int set_cloud(gicpContext* h, int which, const void* d_points, const int64_t* h_offsets, int n_clouds,
               cudaStream_t st) {
@@ -477,9 +491,13 @@ int set_cloud(gicpContext* h, int which, const void* d_points, const int64_t* h_
     }
     if (cs.n_total > 0 && !d_points) return fail("null point array");
     CU(cs.d_offsets.ensure(off32.size() * sizeof(int)));
+    // one small cloud (the reference's own calls): the single-block grid build takes the point count as an argument
+    // and the 12-byte upload with its copy-engine hop disappears from the latency path
+    cs.inline_n = (n_clouds == 1 && latency_path(h, h_offsets, 1)) ? (int)cs.n_total : -1;
     // no stream synchronisation here: a copy from pageable memory is staged by the driver before the call returns,
     // and the staging vector lives in the handle
-    CU(cudaMemcpyAsync(cs.d_offsets.p, off32.data(), off32.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (cs.inline_n < 0)
+        CU(cudaMemcpyAsync(cs.d_offsets.p, off32.data(), off32.size() * sizeof(int), cudaMemcpyHostToDevice, st));
 
     const double h_knn = auto_knn_cell(h);
     const double h_nn = auto_nn_cell(h);
@@ -636,10 +654,20 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
     if (objective_args<D, Real>(h, oa, bpp, true)) return 1;
     const int np = h->src.n_clouds;
     h->last_stream = st;
-    if (ensure_state<D, Real>(h, h_T0, d_T, d_T_hist, d_n_outer, d_converged, st)) return 1;
-    // last iteration's match per source point (bounds the next search); -1 = none yet
-    CU(cudaMemsetAsync(h->prev_match.p, 0xFF, (size_t)std::max<int64_t>(h->src.n_total, 1) * sizeof(int), st));
-    CU(cudaMemsetAsync(h->slack.p, 0, (size_t)std::max<int64_t>(h->src.n_total, 1) * sizeof(float), st));
+    // Small pairs (every source cloud fits one block): the whole outer loop in one launch (fused.cuh).  Not with a
+    // communicator (the all-reduce sits between the stages) and not while per-stage timing is on.
+    const bool fused = !(h->comm && np == 1) && !h->prof_on && h->src.max_n <= OBJ_THREADS * OBJ_MAX_PPT &&
+                       !(getenv("GICP_FUSED_LOOP") && atoi(getenv("GICP_FUSED_LOOP")) == 0);
+    // without a start transform the fused loop initialises its pair itself (state, match and slack arrays)
+    const bool self_init = fused && !h_T0;
+    if (self_init) {
+        CU(h->state.ensure((size_t)np * sizeof(PairState)));
+    } else {
+        if (ensure_state<D, Real>(h, h_T0, d_T, d_T_hist, d_n_outer, d_converged, st)) return 1;
+        // last iteration's match per source point (bounds the next search); -1 = none yet
+        CU(cudaMemsetAsync(h->prev_match.p, 0xFF, (size_t)std::max<int64_t>(h->src.n_total, 1) * sizeof(int), st));
+        CU(cudaMemsetAsync(h->slack.p, 0, (size_t)std::max<int64_t>(h->src.n_total, 1) * sizeof(float), st));
+    }
     oa.use_prev = 1;
     oa.slack = (getenv("GICP_NO_SKIP") && atoi(getenv("GICP_NO_SKIP"))) ? nullptr : h->slack.as<float>();
     SolveArgs sa;
@@ -660,11 +688,7 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
     sa.n_active = h->n_active.as<int>();
     sa.active_list = nullptr;
     sa.n_list = nullptr;
-    // Small pairs (every source cloud fits one block): the whole outer loop in one launch (fused.cuh).  Not with a
-    // communicator (the all-reduce sits between the stages) and not while per-stage timing is on.
-    const bool sharded_pair = h->comm && np == 1;
-    if (!sharded_pair && !h->prof_on && h->src.max_n <= OBJ_THREADS * OBJ_MAX_PPT &&
-        !(getenv("GICP_FUSED_LOOP") && atoi(getenv("GICP_FUSED_LOOP")) == 0)) {
+    if (fused) {
         oa.ppt = std::max(1, (h->src.max_n + OBJ_THREADS - 1) / OBJ_THREADS);
         oa.blocks_per_pair = 1;
         sa.blocks_per_pair = 1;
@@ -672,7 +696,8 @@ int do_register(gicpContext* h, const double* h_T0, double* d_T, int* d_n_outer,
         const size_t smem = obj_smem(oa.ppt);
         CU(cudaFuncSetAttribute(register_loop_kernel<D, Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ProfScope prof(h, GICP_STAGE_CORRESPOND, st);
-        register_loop_kernel<D, Real><<<np, OBJ_THREADS, smem, st>>>(oa, sa);
+        register_loop_kernel<D, Real><<<np, OBJ_THREADS, smem, st>>>(oa, sa,
+                                                                     self_init ? h->tgt.knn.bbox.as<double>() : nullptr);
         h->launches += 1;
         CU(cudaGetLastError());
         return 0;
@@ -963,21 +988,6 @@ int gicpSetSource(gicpHandle h, const void* d_points, const int64_t* h_offsets, 
     if (!h_offsets) return fail("null offsets");
     return DISPATCH(h, set_cloud, h, GICP_SOURCE, d_points, h_offsets, n_clouds, (cudaStream_t)stream);
 }
-
-namespace {
-// true when set_cloud takes the latency path for these clouds (small_grid_kernel + one k-NN launch): that path
-// touches only the side's own buffers, none of the handle's shared scratch (same conditions as build_grid / launch_knn)
-bool latency_path(const gicpContext* h, const int64_t* off, int n_clouds) {
-    if (getenv("GICP_SMALL_GRID") && atoi(getenv("GICP_SMALL_GRID")) == 0) return false;
-    if (n_clouds <= 0 || off[0] != 0 || h->prm.max_cells_per_cloud > (1LL << 20)) return false;
-    int64_t max_n = 0;
-    for (int i = 1; i <= n_clouds; ++i) {
-        if (off[i] < off[i - 1]) return false;
-        max_n = std::max<int64_t>(max_n, off[i] - off[i - 1]);
-    }
-    return max_n <= SMALL_GRID_MAX && off[n_clouds] > 0 && off[n_clouds] <= 65536;
-}
-}  // namespace
 
 int gicpSetPair(gicpHandle h, const void* d_target, const int64_t* h_target_offsets, const void* d_source,
                 const int64_t* h_source_offsets, int32_t n_clouds, void* stream) {

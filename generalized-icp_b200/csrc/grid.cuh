@@ -209,12 +209,13 @@ template <int D, typename Real>
 __global__ void __launch_bounds__(SMALL_GRID_THREADS) small_grid_kernel(
     const Real* __restrict__ pts, const int* __restrict__ offsets, double h_target, long long budget,
     CloudMeta* __restrict__ meta, double* __restrict__ bbox_out, int* __restrict__ lut, int* __restrict__ cell_start,
-    PRec<Real>* __restrict__ spts, int* __restrict__ inv_perm, int is_last_cloud_total_cells) {
+    PRec<Real>* __restrict__ spts, int* __restrict__ inv_perm, int is_last_cloud_total_cells, int inline_n) {
     __shared__ unsigned s_key[SMALL_GRID_MAX];   // (cell code << 11) | input index
     __shared__ double s_lo[SMALL_GRID_THREADS / 32][3], s_hi[SMALL_GRID_THREADS / 32][3];
     __shared__ CloudMeta s_meta;
     const int cloud = blockIdx.x;
-    const int b = offsets[cloud], e = offsets[cloud + 1];
+    // inline_n >= 0: a single cloud of that many points (the offsets array has not been uploaded)
+    const int b = inline_n >= 0 ? 0 : offsets[cloud], e = inline_n >= 0 ? inline_n : offsets[cloud + 1];
     const int n = e - b;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     // ---- bounding box ----

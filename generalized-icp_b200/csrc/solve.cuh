@@ -497,14 +497,10 @@ __global__ void __launch_bounds__(COMPACT_THREADS) compact_active_kernel(const P
     if (threadIdx.x == 0) *n_list = s_base;
 }
 
-// initialise the per-pair state (gicp.py:107-110): T = T0 or identity, last_loss = inf
+// initialise the state of one pair (gicp.py:107-110): T = T0 or identity, last_loss = inf
 template <int D>
-__global__ void init_state_kernel(PairState* state, const double* T0, const double* tgt_bbox, int n_pairs,
-                                  double* d_T, double* d_T_hist, int max_iterations, int* d_n_outer,
-                                  int* d_converged, int* n_active) {
-    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pair == 0 && n_active) *n_active = n_pairs;   // pairs still iterating (K4 counts it down, the host polls it)
-    if (pair >= n_pairs) return;
+__device__ inline void init_pair_state(PairState* state, const double* T0, const double* tgt_bbox, int pair, double* d_T,
+                                       double* d_T_hist, int max_iterations, int* d_n_outer, int* d_converged) {
     PairState st;
     for (int i = 0; i < 9; ++i) st.R[i] = (i % 4 == 0) ? 1.0 : 0.0;
     for (int i = 0; i < 3; ++i) { st.t[i] = 0.0; st.mu[i] = 0.5 * (tgt_bbox[pair * 6 + i] + tgt_bbox[pair * 6 + 3 + i]); }
@@ -529,6 +525,16 @@ __global__ void init_state_kernel(PairState* state, const double* T0, const doub
     if (d_T_hist) write_T<D>(d_T_hist + (size_t)pair * (max_iterations + 1) * (D + 1) * (D + 1), st);
     if (d_n_outer) d_n_outer[pair] = 0;
     if (d_converged) d_converged[pair] = -1;
+}
+
+template <int D>
+__global__ void init_state_kernel(PairState* state, const double* T0, const double* tgt_bbox, int n_pairs,
+                                  double* d_T, double* d_T_hist, int max_iterations, int* d_n_outer,
+                                  int* d_converged, int* n_active) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair == 0 && n_active) *n_active = n_pairs;   // pairs still iterating (K4 counts it down, the host polls it)
+    if (pair >= n_pairs) return;
+    init_pair_state<D>(state, T0, tgt_bbox, pair, d_T, d_T_hist, max_iterations, d_n_outer, d_converged);
 }
 
 }  // namespace gicp

@@ -146,7 +146,7 @@ class GicpEngine:
     def register_pair_host(self, src, tgt):
         """One pair given as HOST arrays, everything the reference's 7-tuple needs back as host numpy arrays, with
         the fewest host<->device round trips: both clouds travel in ONE staged copy (pinned, cached), every output
-        of gicpRegister + gicpCovariances lands in two device buffers (doubles, ints) that come back in two copies.
+        of gicpRegister + gicpCovariances lands in one cached device buffer that comes back in one copy.
         (`set_target` + `set_source` + `register` + `covariances` issue 9 small copies / synchronisations for the
         same result, which is most of the wall time of a 360-point registration.)  Returns a dict: T, T_hist, loss_hist,
         inliers, n_outer, converged_at, src_cov0, tgt_cov."""
@@ -155,6 +155,8 @@ class GicpEngine:
         np_dt = np.float64 if self.storage == "f64" else np.float32
         src = np.ascontiguousarray(src, dtype=np_dt)
         tgt = np.ascontiguousarray(tgt, dtype=np_dt)
+        if src.ndim != 2 or tgt.ndim != 2 or src.shape[1] != d or tgt.shape[1] != d:
+            raise ValueError(f"expected (N, {d}) points, got {src.shape} and {tgt.shape}")
         n_s, n_t = src.shape[0], tgt.shape[0]
         pad_s = (n_s + 3) & ~3                                  # keeps the target rows 16-byte aligned
         rows = pad_s + n_t
@@ -167,7 +169,15 @@ class GicpEngine:
         hv[:n_s] = src
         hv[pad_s:rows] = tgt
         self._pp_dev[:rows].copy_(self._pp_host[:rows], non_blocking=True)
-        self.set_pair(self._pp_dev[pad_s:rows], self._pp_dev[:n_s])
+        # both clouds through gicpSetPair, straight from the staging buffer (no per-call tensor views or checks: the
+        # host's submission time is on the critical path of a 90-point registration)
+        vp = C.c_void_p
+        st = self._stream()
+        base, row_bytes = self._pp_dev.data_ptr(), d * self._pp_dev.element_size()
+        self._keep[TARGET] = self._keep[SOURCE] = self._pp_dev
+        self._n[TARGET], self._n[SOURCE] = (n_t, 1), (n_s, 1)
+        _lib.check(self.lib.gicpSetPair(self._h, vp(base + pad_s * row_bytes), (C.c_int64 * 2)(0, n_t), vp(base),
+                                        (C.c_int64 * 2)(0, n_s), 1, st))
         # outputs: [T | loss_hist | T_hist | src_cov | tgt_cov] (f64) followed by [n_outer | converged | inliers] (i32)
         # in ONE cached device buffer with a pinned host mirror: one device->host copy, no fill kernels (the rows the
         # loop did not reach are set to NaN on the host copy)
@@ -184,8 +194,6 @@ class GicpEngine:
             self._po_len = cap
         dp = self._po_dev.data_ptr()
         ip = dp + 8 * nd
-        vp = C.c_void_p
-        st = self._stream()
         _lib.check(self.lib.gicpRegister(self._h, None, vp(dp), vp(ip), vp(ip + 4), vp(dp + 8 * offs[1]),
                                          vp(dp + 8 * offs[2]), vp(ip + 8), st))
         if n_s:

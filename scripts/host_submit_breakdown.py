@@ -46,7 +46,10 @@ for rep in range(3):
         t = stamp("stage into pinned", t)
         eng._pp_dev[:rows].copy_(eng._pp_host[:rows], non_blocking=True)
         t = stamp("h2d submit", t)
-        eng.set_pair(eng._pp_dev[pad_s:rows], eng._pp_dev[:n_s])
+        st = eng._stream()
+        base, row_bytes = eng._pp_dev.data_ptr(), d * eng._pp_dev.element_size()
+        _lib.check(eng.lib.gicpSetPair(eng._h, vp(base + pad_s * row_bytes), (C.c_int64 * 2)(0, n_t), vp(base),
+                                       (C.c_int64 * 2)(0, n_s), 1, st))
         t = stamp("set_pair", t)
         sizes = [d1 * d1, mi, (mi + 1) * d1 * d1, n_s * d * d, n_t * d * d]
         offs = [0]
@@ -56,7 +59,6 @@ for rep in range(3):
         tot = nd + (2 + mi + 1) // 2
         dp = eng._po_dev.data_ptr()
         ip = dp + 8 * nd
-        st = eng._stream()
         _lib.check(eng.lib.gicpRegister(eng._h, None, vp(dp), vp(ip), vp(ip + 4), vp(dp + 8 * offs[1]),
                                         vp(dp + 8 * offs[2]), vp(ip + 8), st))
         t = stamp("gicpRegister", t)
