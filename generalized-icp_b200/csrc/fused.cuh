@@ -17,32 +17,37 @@ __global__ void __launch_bounds__(OBJ_THREADS) register_loop_kernel(const ObjArg
                                                                     const double* init_bbox) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NRED = Dim<D>::NRED;
+    // the pair's state and the reduced form live in shared memory for the whole loop: on the multi-launch path they
+    // travel through global memory between the stages, which costs a block that owns the pair four dependent L2 round
+    // trips per outer iteration
     __shared__ double s_sum[NRED];
     __shared__ SolveScratch<D> s_sc;
+    __shared__ PairState s_state;
     const int pair = blockIdx.x;
     WarpStage<Real> ws = obj_warp_stage<Real>(smem_raw);   // one mbarrier per warp for the whole loop
     if (init_bbox) {
         if (threadIdx.x == 0)
-            init_pair_state<D>(sa.state, nullptr, init_bbox, pair, sa.d_T, sa.d_T_hist,
-                               sa.max_iterations, sa.d_n_outer, sa.d_converged);
+            init_pair_state<D>(&s_state, nullptr, init_bbox, pair, sa.d_T, sa.d_T_hist, sa.max_iterations, sa.d_n_outer,
+                               sa.d_converged);
         const CloudMeta ms = oa.src_meta[pair];
         for (int s = ms.pt_begin + (int)threadIdx.x; s < ms.pt_end; s += OBJ_THREADS) {
             oa.match[s] = -1;
             if (oa.slack) oa.slack[s] = 0.f;
         }
-        __syncthreads();
+    } else if (threadIdx.x == 0) {
+        s_state = sa.state[pair];                          // initialised by init_state_kernel (start transform given)
     }
+    __syncthreads();
     for (int it = 0; it < sa.max_iterations; ++it) {
-        correspond_block<D, Real>(oa, pair, 0, ws, smem_raw);
+        correspond_block<D, Real>(oa, pair, 0, ws, smem_raw, &s_state);
         __syncthreads();                                   // this block's matches are visible to the block
-        accumulate_block<D, Real>(oa, pair, 0);            // -> partial[pair][0][NRED]
+        accumulate_block<D, Real>(oa, pair, 0, &s_state, s_sum);
         __syncthreads();
-        if (threadIdx.x < NRED) s_sum[threadIdx.x] = oa.partial[(size_t)pair * NRED + threadIdx.x];
-        __syncthreads();
-        if (threadIdx.x < 32) solve_pair<D>(sa, pair, sa.state[pair], s_sum, s_sc);   // warp 0, all lanes
-        __syncthreads();                                   // the new state (global) is visible to the block
-        if (sa.state[pair].status != PAIR_ACTIVE) break;
+        if (threadIdx.x < 32) solve_pair<D>(sa, pair, s_state, s_sum, s_sc, &s_state);   // warp 0, all lanes
+        __syncthreads();                                   // the new state is visible to the block
+        if (s_state.status != PAIR_ACTIVE) break;
     }
+    if (threadIdx.x == 0) sa.state[pair] = s_state;        // what later calls on the handle read
 }
 
 }  // namespace gicp

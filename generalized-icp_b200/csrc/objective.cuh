@@ -72,10 +72,11 @@ __device__ __forceinline__ int obj_pair_of_block(const ObjArgs<Real>& a) {
 // One block of the search: points [bx * ppt * OBJ_THREADS, ...) of pair `pair`.  `ws` is the warp's TMA stage
 // (buffer, mbarrier, phase); it is carried by the caller so that the fused registration loop (register_loop_kernel)
 // can call this once per outer iteration on one initialised mbarrier.
+// `stp`: the pair's state (a.state + pair; the fused loop keeps it in shared memory instead).
 template <int D, typename Real>
 __device__ __forceinline__ void correspond_block(const ObjArgs<Real>& a, const int pair, const int bx,
-                                                 WarpStage<Real>& ws, unsigned char* smem_raw) {
-    const PairState st = a.state[pair];
+                                                 WarpStage<Real>& ws, unsigned char* smem_raw, const PairState* stp) {
+    const PairState st = *stp;
     if (!a.ignore_status && st.status != PAIR_ACTIVE) return;
 
     double R[D][D], t[D];
@@ -401,16 +402,18 @@ __global__ void __launch_bounds__(OBJ_THREADS, (D == 3 && sizeof(Real) == 4) ? 1
     const int pair = obj_pair_of_block(a);
     if (pair < 0) return;
     WarpStage<Real> ws = obj_warp_stage<Real>(smem_raw);
-    correspond_block<D, Real>(a, pair, blockIdx.x, ws, smem_raw);
+    correspond_block<D, Real>(a, pair, blockIdx.x, ws, smem_raw, a.state + pair);
 }
 
-// One block of the accumulation: points [bx * ppt * OBJ_THREADS, ...) of pair `pair` -> partial[pair][bx][NRED]
+// One block of the accumulation: points [bx * ppt * OBJ_THREADS, ...) of pair `pair` -> out[NRED]
+// (a.partial[pair][bx]; the fused loop passes its shared-memory sum and state instead)
 template <int D, typename Real>
-__device__ __forceinline__ void accumulate_block(const ObjArgs<Real>& a, const int pair, const int bx) {
+__device__ __forceinline__ void accumulate_block(const ObjArgs<Real>& a, const int pair, const int bx,
+                                                 const PairState* stp, double* out) {
     using DD = Dim<D>;
     using AccT = Real;
     constexpr int NP = DD::NP, NS = DD::NS, NH = DD::NH, NQ = DD::NQ, NRED = DD::NRED;
-    const PairState st = a.state[pair];
+    const PairState st = *stp;
     if (!a.ignore_status && st.status != PAIR_ACTIVE) return;
 
     double R[D][D], t[D];
@@ -439,7 +442,7 @@ __device__ __forceinline__ void accumulate_block(const ObjArgs<Real>& a, const i
     if (begin >= end) {
         // empty source cloud (or empty shard slice): nothing to gather - the pipeline below would read the record
         // before `begin`.  The pair's partial rows are zero.
-        if (threadIdx.x < NRED) a.partial[((size_t)pair * a.blocks_per_pair + bx) * NRED + threadIdx.x] = 0.0;
+        if (threadIdx.x < NRED) out[threadIdx.x] = 0.0;
         return;
     }
     AccT acc[NQ];
@@ -626,7 +629,7 @@ __device__ __forceinline__ void accumulate_block(const ObjArgs<Real>& a, const i
 #pragma unroll
             for (int w = 0; w < OBJ_THREADS / 32; ++w) r += s_red[w][threadIdx.x];
         }
-        a.partial[((size_t)pair * a.blocks_per_pair + bx) * NRED + threadIdx.x] = r;
+        out[threadIdx.x] = r;
     }
 }
 
@@ -636,7 +639,8 @@ template <int D, typename Real>
 __global__ void __launch_bounds__(OBJ_THREADS, (sizeof(Real) == 8 && D == 3) ? 2 : 4) accumulate_kernel(const ObjArgs<Real> a) {
     const int pair = obj_pair_of_block(a);
     if (pair < 0) return;
-    accumulate_block<D, Real>(a, pair, blockIdx.x);
+    accumulate_block<D, Real>(a, pair, blockIdx.x, a.state + pair,
+                              a.partial + ((size_t)pair * a.blocks_per_pair + blockIdx.x) * Dim<D>::NRED);
 }
 
 }  // namespace gicp

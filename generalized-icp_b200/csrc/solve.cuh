@@ -34,29 +34,34 @@ template <int D> struct SolveScratch {
     int go;
 };
 
-template <int N> __device__ inline bool cholesky_solve(double A[N][N], double b[N]) {
-    // in-place LL^T; returns false when A is not positive definite
+// Solves A x = b for a symmetric positive definite A through A = L D L^T (in place: unit lower L below the diagonal, D
+// on it); returns false when A is not positive definite (same pivots as a Cholesky factorisation).  No square roots and
+// one reciprocal per pivot: in float64 a division or a square root is a ~20-instruction dependent chain, and the damped
+// solve sits on the critical path of every LM iteration of a small registration (one lane, everybody else waits).
+template <int N> __device__ inline bool spd_solve(double A[N][N], double b[N]) {
+    double inv[N];
     for (int j = 0; j < N; ++j) {
         double d = A[j][j];
-        for (int k = 0; k < j; ++k) d -= A[j][k] * A[j][k];
+        for (int k = 0; k < j; ++k) d -= A[j][k] * A[j][k] * A[k][k];
         if (!(d > 0.0) || !isfinite(d)) return false;
-        d = sqrt(d);
         A[j][j] = d;
+        inv[j] = 1.0 / d;
         for (int i = j + 1; i < N; ++i) {
             double s = A[i][j];
-            for (int k = 0; k < j; ++k) s -= A[i][k] * A[j][k];
-            A[i][j] = s / d;
+            for (int k = 0; k < j; ++k) s -= A[i][k] * A[j][k] * A[k][k];
+            A[i][j] = s * inv[j];
         }
     }
-    for (int i = 0; i < N; ++i) {
+    for (int i = 0; i < N; ++i) {          // L y = b
         double s = b[i];
         for (int k = 0; k < i; ++k) s -= A[i][k] * b[k];
-        b[i] = s / A[i][i];
+        b[i] = s;
     }
-    for (int i = N - 1; i >= 0; --i) {
+    for (int i = 0; i < N; ++i) b[i] *= inv[i];   // D z = y
+    for (int i = N - 1; i >= 0; --i) {     // L^T x = z
         double s = b[i];
         for (int k = i + 1; k < N; ++k) s -= A[k][i] * b[k];
-        b[i] = s / A[i][i];
+        b[i] = s;
     }
     return true;
 }
@@ -143,7 +148,7 @@ __device__ inline void inner_solve_2d(const double* Hq, const double* G, double 
                 L[x][x] += lam * A[x][x];
                 step[x] = -g[x];
             }
-            if (!cholesky_solve<3>(L, step)) { lam = fmax(lam * 10.0, 1e-6); continue; }
+            if (!spd_solve<3>(L, step)) { lam = fmax(lam * 10.0, 1e-6); continue; }
             const double thn = th + step[2];
             double sn_n, cs_n;
             sincos(thn, &sn_n, &cs_n);
@@ -259,7 +264,7 @@ __device__ void inner_solve_warp(SolveScratch<D>& sc, const double* G, double c0
                         L[x][x] += lam * sc.A[x][x];
                         step[x] = -sc.g[x];
                     }
-                    if (!cholesky_solve<NPAR>(L, step)) { lam = fmax(lam * 10.0, 1e-6); continue; }
+                    if (!spd_solve<NPAR>(L, step)) { lam = fmax(lam * 10.0, 1e-6); continue; }
                     double dRn[D][D], dtn[D], thn;
                     compose_rotation<D>(step + D, sc.dR, sc.dtheta, dRn, &thn);
                     for (int c_ = 0; c_ < D; ++c_) {
@@ -359,8 +364,10 @@ __global__ void presum_kernel(const double* __restrict__ partial, int blocks_per
 
 // Tail of one outer iteration of one pair, run by ONE WARP (all 32 lanes call it): `sums` is the pair's summed reduced
 // form ([NRED] doubles, shared memory), `sc` the warp's scratch, `st` the pair's state (read by the caller).
+// The updated state goes to `stp` (a.state + pair; the fused loop keeps the state in shared memory).
 template <int D>
-__device__ void solve_pair(const SolveArgs& a, const int pair, PairState st, const double* sums, SolveScratch<D>& sc) {
+__device__ void solve_pair(const SolveArgs& a, const int pair, PairState st, const double* sums, SolveScratch<D>& sc,
+                           PairState* stp) {
     using DD = Dim<D>;
     constexpr int NQ = DD::NQ, DN2 = SolveScratch<D>::DN * SolveScratch<D>::DN;
     const int lane = threadIdx.x & 31;
@@ -431,7 +438,7 @@ __device__ void solve_pair(const SolveArgs& a, const int pair, PairState st, con
     }
     write_T<D>(a.d_T + (size_t)pair * (D + 1) * (D + 1), st);
     a.d_converged[pair] = st.converged_at;
-    a.state[pair] = st;
+    *stp = st;
     if (st.status != PAIR_ACTIVE && a.n_active) atomicSub(a.n_active, 1);
 }
 
@@ -465,7 +472,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) solve_kernel(const SolveArgs
         }
         return;
     }
-    solve_pair<D>(a, pair, st, s_red[warp], s_sc[warp]);
+    solve_pair<D>(a, pair, st, s_red[warp], s_sc[warp], a.state + pair);
 }
 
 // One block: the pairs that are still iterating, in ascending order -> list[0 .. *n_list)
@@ -499,7 +506,7 @@ __global__ void __launch_bounds__(COMPACT_THREADS) compact_active_kernel(const P
 
 // initialise the state of one pair (gicp.py:107-110): T = T0 or identity, last_loss = inf
 template <int D>
-__device__ inline void init_pair_state(PairState* state, const double* T0, const double* tgt_bbox, int pair, double* d_T,
+__device__ inline void init_pair_state(PairState* stp, const double* T0, const double* tgt_bbox, int pair, double* d_T,
                                        double* d_T_hist, int max_iterations, int* d_n_outer, int* d_converged) {
     PairState st;
     for (int i = 0; i < 9; ++i) st.R[i] = (i % 4 == 0) ? 1.0 : 0.0;
@@ -520,7 +527,7 @@ __device__ inline void init_pair_state(PairState* state, const double* T0, const
     st.status = PAIR_ACTIVE;
     st.converged_at = -1;
     st.pad = 0;
-    state[pair] = st;
+    *stp = st;
     if (d_T) write_T<D>(d_T + (size_t)pair * (D + 1) * (D + 1), st);
     if (d_T_hist) write_T<D>(d_T_hist + (size_t)pair * (max_iterations + 1) * (D + 1) * (D + 1), st);
     if (d_n_outer) d_n_outer[pair] = 0;
@@ -534,7 +541,7 @@ __global__ void init_state_kernel(PairState* state, const double* T0, const doub
     const int pair = blockIdx.x * blockDim.x + threadIdx.x;
     if (pair == 0 && n_active) *n_active = n_pairs;   // pairs still iterating (K4 counts it down, the host polls it)
     if (pair >= n_pairs) return;
-    init_pair_state<D>(state, T0, tgt_bbox, pair, d_T, d_T_hist, max_iterations, d_n_outer, d_converged);
+    init_pair_state<D>(state + pair, T0, tgt_bbox, pair, d_T, d_T_hist, max_iterations, d_n_outer, d_converged);
 }
 
 }  // namespace gicp
