@@ -131,12 +131,22 @@ constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_INT8 = 0;
 
 }  // namespace
 
+// scratch of one set-up (grid build + k-NN) in flight: sort keys / values, CUB storage, bounding-box partials, the
+// k-NN overflow hand-over list
+struct SetupScratch {
+    DevBuf keys, keys_alt, vals, vals_alt, cub_tmp, bbox_part, ovf_count, ovf_list;
+    void release() {
+        for (DevBuf* b : {&keys, &keys_alt, &vals, &vals_alt, &cub_tmp, &bbox_part, &ovf_count, &ovf_list}) b->release();
+    }
+};
+
 struct gicpContext {
     int device = 0, dim = 2, storage = GICP_STORAGE_F64;
     gicpParams prm;
     CloudSet src, tgt;
-    DevBuf keys, keys_alt, vals, vals_alt, cub_tmp, cell_count, bbox_part;
-    DevBuf state, partial, partial2, red, T_dev, n_active, prev_match, slack, ovf_count, ovf_list, active_list;
+    // [0]: every call on the caller's stream; [1]: the source side of gicpSetPair while it runs on the internal stream
+    SetupScratch scr[2];
+    DevBuf state, partial, partial2, red, T_dev, n_active, prev_match, slack, active_list;
     static constexpr int NPOLL = 8;
     int* h_poll = nullptr;  // pinned [NPOLL]: progress polls in flight
     cudaEvent_t poll_ev[NPOLL] = {};
@@ -190,7 +200,7 @@ struct ProfScope {
 };
 
 template <int D, typename Real>
-int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, cudaStream_t st) {
+int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, cudaStream_t st, SetupScratch& sc) {
     const int nc = cs.n_clouds;
     const int64_t n = cs.n_total;
     long long budget = h->prm.max_cells_per_cloud;
@@ -214,16 +224,16 @@ int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, cudaStrea
     g.total_cells = budget * nc;
     g.h_target = h_target;
     const int chunks = std::max(1, (cs.max_n + BBOX_THREADS * BBOX_ITEMS - 1) / (BBOX_THREADS * BBOX_ITEMS));
-    CU(h->bbox_part.ensure((size_t)nc * chunks * 6 * sizeof(double)));
+    CU(sc.bbox_part.ensure((size_t)nc * chunks * 6 * sizeof(double)));
     CU(g.meta.ensure((size_t)nc * sizeof(CloudMeta)));
     CU(g.bbox.ensure((size_t)nc * 6 * sizeof(double)));
     CU(g.cell_start.ensure((size_t)(g.total_cells + 1) * sizeof(int)));
     CU(g.spts.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(PRec<Real>)));
     CU(g.inv_perm.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(int)));
-    CU(h->keys.ensure((size_t)std::max<int64_t>(n, 1) * 4));
-    CU(h->keys_alt.ensure((size_t)std::max<int64_t>(n, 1) * 4));
-    CU(h->vals.ensure((size_t)std::max<int64_t>(n, 1) * 4));
-    CU(h->vals_alt.ensure((size_t)std::max<int64_t>(n, 1) * 4));
+    CU(sc.keys.ensure((size_t)std::max<int64_t>(n, 1) * 4));
+    CU(sc.keys_alt.ensure((size_t)std::max<int64_t>(n, 1) * 4));
+    CU(sc.vals.ensure((size_t)std::max<int64_t>(n, 1) * 4));
+    CU(sc.vals_alt.ensure((size_t)std::max<int64_t>(n, 1) * 4));
     const Real* pts = static_cast<const Real*>(cs.raw);
     const int* offs = cs.d_offsets.as<int>();
     ProfScope prof(h, GICP_STAGE_GRID, st);
@@ -242,8 +252,8 @@ int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, cudaStrea
         return 0;
     }
 
-    bbox_partial_kernel<D, Real><<<dim3(chunks, nc), BBOX_THREADS, 0, st>>>(pts, offs, h->bbox_part.as<double>(), chunks);
-    grid_meta_kernel<D><<<(nc + 3) / 4, 128, 0, st>>>(h->bbox_part.as<double>(), chunks, offs, nc, h_target, budget,
+    bbox_partial_kernel<D, Real><<<dim3(chunks, nc), BBOX_THREADS, 0, st>>>(pts, offs, sc.bbox_part.as<double>(), chunks);
+    grid_meta_kernel<D><<<(nc + 3) / 4, 128, 0, st>>>(sc.bbox_part.as<double>(), chunks, offs, nc, h_target, budget,
                                                           g.meta.as<CloudMeta>(), g.bbox.as<double>());
     CU(g.lut.ensure((size_t)nc * 3 * GICP_LUT_N * sizeof(int)));
     morton_lut_kernel<<<dim3(3 * GICP_LUT_N / 256, nc), 256, 0, st>>>(g.meta.as<CloudMeta>(), g.lut.as<int>());
@@ -252,28 +262,28 @@ int build_grid(gicpContext* h, CloudSet& cs, Grid& g, double h_target, cudaStrea
     h->launches += 3;
     if (n > 0) {
         const int bx = (cs.max_n + 255) / 256;
-        cell_key_kernel<D, Real><<<dim3(bx, nc), 256, 0, st>>>(pts, g.meta.as<CloudMeta>(), h->keys.as<unsigned>(),
-                                                               h->vals.as<int>(), g.cell_start.as<int>());
+        cell_key_kernel<D, Real><<<dim3(bx, nc), 256, 0, st>>>(pts, g.meta.as<CloudMeta>(), sc.keys.as<unsigned>(),
+                                                               sc.vals.as<int>(), g.cell_start.as<int>());
         h->launches += 1;
     }
     {   // cell_start = exclusive scan of the histogram
         size_t tmp = 0;
         CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, g.cell_start.as<int>(), g.cell_start.as<int>(),
                                          (int)(g.total_cells + 1), st));
-        CU(h->cub_tmp.ensure(tmp));
-        CU(cub::DeviceScan::ExclusiveSum(h->cub_tmp.p, tmp, g.cell_start.as<int>(), g.cell_start.as<int>(),
+        CU(sc.cub_tmp.ensure(tmp));
+        CU(cub::DeviceScan::ExclusiveSum(sc.cub_tmp.p, tmp, g.cell_start.as<int>(), g.cell_start.as<int>(),
                                          (int)(g.total_cells + 1), st));
         h->launches += 2;
     }
     if (n > 0) {
         int bits = 1;
         while ((1LL << bits) < g.total_cells) ++bits;
-        cub::DoubleBuffer<unsigned> dk(h->keys.as<unsigned>(), h->keys_alt.as<unsigned>());
-        cub::DoubleBuffer<int> dv(h->vals.as<int>(), h->vals_alt.as<int>());
+        cub::DoubleBuffer<unsigned> dk(sc.keys.as<unsigned>(), sc.keys_alt.as<unsigned>());
+        cub::DoubleBuffer<int> dv(sc.vals.as<int>(), sc.vals_alt.as<int>());
         size_t tmp = 0;
         CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)n, 0, bits, st));
-        CU(h->cub_tmp.ensure(tmp));
-        CU(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp, dk, dv, (int)n, 0, bits, st));
+        CU(sc.cub_tmp.ensure(tmp));
+        CU(cub::DeviceRadixSort::SortPairs(sc.cub_tmp.p, tmp, dk, dv, (int)n, 0, bits, st));
         h->launches += (bits + 7) / 8 + 2;
         const int bx = (cs.max_n + 255) / 256;
         gather_sorted_kernel<D, Real><<<dim3(bx, nc), 256, 0, st>>>(pts, g.meta.as<CloudMeta>(), dv.Current(),
@@ -352,7 +362,8 @@ __global__ void rotated_cov_kernel(const CloudMeta* __restrict__ meta, const PRe
 }
 
 template <int D, typename Real>
-int launch_knn(gicpContext* h, CloudSet& cs, int* d_idx, double* d_dist, cudaStream_t st, int slice_b, int slice_e) {
+int launch_knn(gicpContext* h, CloudSet& cs, int* d_idx, double* d_dist, cudaStream_t st, int slice_b, int slice_e,
+               SetupScratch& sc) {
     KnnArgs<Real> a;
     a.meta = cs.knn.meta.as<CloudMeta>();
     a.cell_start = cs.knn.cell_start.as<int>();
@@ -375,10 +386,10 @@ int launch_knn(gicpContext* h, CloudSet& cs, int* d_idx, double* d_dist, cudaStr
     dim3 grid(bx, cs.n_clouds);
     // fast path's overflow hand-over: worst case every warp
     const long long n_chunks = (long long)bx * KNN_WARPS * cs.n_clouds;
-    CU(h->ovf_count.ensure(sizeof(int)));
-    CU(h->ovf_list.ensure((size_t)n_chunks * sizeof(int2)));
-    a.overflow_count = h->ovf_count.as<int>();
-    a.overflow_list = h->ovf_list.as<int2>();
+    CU(sc.ovf_count.ensure(sizeof(int)));
+    CU(sc.ovf_list.ensure((size_t)n_chunks * sizeof(int2)));
+    a.overflow_count = sc.ovf_count.as<int>();
+    a.overflow_list = sc.ovf_list.as<int2>();
     a.overflow_cap = (int)std::min<long long>(n_chunks, INT_MAX);
     // latency mode (a few small clouds): the general kernel alone - one launch, no overflow hand-over
     const bool latency_mode = cs.max_n <= SMALL_GRID_MAX && cs.n_total <= 65536 &&
@@ -405,7 +416,7 @@ int launch_knn(gicpContext* h, CloudSet& cs, int* d_idx, double* d_dist, cudaStr
         return 0;
     }
     if (fast) {
-        CU(cudaMemsetAsync(h->ovf_count.p, 0, sizeof(int), st));
+        CU(cudaMemsetAsync(sc.ovf_count.p, 0, sizeof(int), st));
         CU(cudaFuncSetAttribute(knn_hist_kernel<D, Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
         CU(cudaFuncSetAttribute(knn_hist_kernel<D, Real>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         const size_t smem_l = (size_t)KNN_WARPS * KNN_LANE_WARP_SMEM;
@@ -469,7 +480,8 @@ bool latency_path(const gicpContext* h, const int64_t* off, int n_clouds) {
 
 template <int D, typename Real>
 int set_cloud(gicpContext* h, int which, const void* d_points, const int64_t* h_offsets, int n_clouds,
-              cudaStream_t st) {
+              cudaStream_t st, int scratch_slot) {
+    SetupScratch& sc = h->scr[scratch_slot];
     CloudSet& cs = which == GICP_TARGET ? h->tgt : h->src;
     cs.ready = false;
     h->last_stream = st;
@@ -506,7 +518,7 @@ int set_cloud(gicpContext* h, int which, const void* d_points, const int64_t* h_
     // on the bench workload (k-NN cell 1.25 m, search cell 1.0 m): K3a 14.97 vs 15.16 ms per 512 pairs - no loss.
     cs.shared = h_knn <= 2.0 * h_nn && h_knn >= h->prm.max_distance_correspondence / 8.0 &&
                 !(getenv("GICP_SHARED_GRID") && atoi(getenv("GICP_SHARED_GRID")) == 0);
-    if (build_grid<D, Real>(h, cs, cs.knn, h_knn, st)) return 1;
+    if (build_grid<D, Real>(h, cs, cs.knn, h_knn, st, sc)) return 1;
     CU(cs.cov_knn.ensure((size_t)std::max<int64_t>(cs.n_total, 1) * ns_of(D) * sizeof(Real)));
 
     // covariances; in sharded mode every rank computes an equal slice (k-NN grid order) of BOTH clouds
@@ -531,7 +543,7 @@ int set_cloud(gicpContext* h, int which, const void* d_points, const int64_t* h_
         const size_t n = (size_t)std::max<int64_t>(cs.n_total, 1);
         fill_cov_kernel<D, Real><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cs.cov_knn.as<Real>(), n, diag);
         h->launches += 1;
-    } else if (launch_knn<D, Real>(h, cs, nullptr, nullptr, st, slice_b, slice_e)) return 1;
+    } else if (launch_knn<D, Real>(h, cs, nullptr, nullptr, st, slice_b, slice_e, sc)) return 1;
     if (sharded && !constant) {
         const size_t bytes = (size_t)per * ns_of(D) * sizeof(Real);
         char* basep = cs.cov_knn.as<char>();
@@ -539,7 +551,7 @@ int set_cloud(gicpContext* h, int which, const void* d_points, const int64_t* h_
         if (rc) return fail("ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
     }
     if (!cs.shared) {   // second ordering for the correspondence stage + the covariances carried over to it
-        if (build_grid<D, Real>(h, cs, cs.nn, h_nn, st)) return 1;
+        if (build_grid<D, Real>(h, cs, cs.nn, h_nn, st, sc)) return 1;
         CU(cs.cov_nn.ensure((size_t)std::max<int64_t>(cs.n_total, 1) * ns_of(D) * sizeof(Real)));
         if (cs.n_total > 0) {
             const int bx = (cs.max_n + 255) / 256;
@@ -850,7 +862,7 @@ int do_knn(gicpContext* h, int which, int* d_idx, double* d_dist, cudaStream_t s
     CloudSet& cs = which == GICP_TARGET ? h->tgt : h->src;
     if (!cs.ready) return fail("cloud not set");
     // re-runs K2 with the index outputs enabled (covariances are rewritten with identical values)
-    return launch_knn<D, Real>(h, cs, d_idx, d_dist, st, -1, -1);
+    return launch_knn<D, Real>(h, cs, d_idx, d_dist, st, -1, -1, h->scr[0]);
 }
 
 template <int D, typename Real>
@@ -949,8 +961,9 @@ int gicpDestroy(gicpHandle h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     h->src.release();
     h->tgt.release();
-    DevBuf* bufs[] = {&h->keys, &h->keys_alt, &h->vals, &h->vals_alt, &h->cub_tmp, &h->cell_count, &h->bbox_part,
-                      &h->state, &h->partial, &h->partial2, &h->red, &h->T_dev, &h->n_active, &h->prev_match, &h->slack, &h->ovf_count, &h->ovf_list, &h->active_list};
+    for (SetupScratch& sc : h->scr) sc.release();
+    DevBuf* bufs[] = {&h->state, &h->partial, &h->partial2, &h->red, &h->T_dev, &h->n_active, &h->prev_match, &h->slack,
+                      &h->active_list};
     for (DevBuf* b : bufs) b->release();
     if (h->h_poll) cudaFreeHost(h->h_poll);
     for (cudaEvent_t e : h->poll_ev) if (e) cudaEventDestroy(e);
@@ -980,13 +993,13 @@ int gicpSetParams(gicpHandle h, const gicpParams* p) {
 int gicpSetTarget(gicpHandle h, const void* d_points, const int64_t* h_offsets, int32_t n_clouds, void* stream) {
     if (check(h)) return 1;
     if (!h_offsets) return fail("null offsets");
-    return DISPATCH(h, set_cloud, h, GICP_TARGET, d_points, h_offsets, n_clouds, (cudaStream_t)stream);
+    return DISPATCH(h, set_cloud, h, GICP_TARGET, d_points, h_offsets, n_clouds, (cudaStream_t)stream, 0);
 }
 
 int gicpSetSource(gicpHandle h, const void* d_points, const int64_t* h_offsets, int32_t n_clouds, void* stream) {
     if (check(h)) return 1;
     if (!h_offsets) return fail("null offsets");
-    return DISPATCH(h, set_cloud, h, GICP_SOURCE, d_points, h_offsets, n_clouds, (cudaStream_t)stream);
+    return DISPATCH(h, set_cloud, h, GICP_SOURCE, d_points, h_offsets, n_clouds, (cudaStream_t)stream, 0);
 }
 
 int gicpSetPair(gicpHandle h, const void* d_target, const int64_t* h_target_offsets, const void* d_source,
@@ -994,11 +1007,16 @@ int gicpSetPair(gicpHandle h, const void* d_target, const int64_t* h_target_offs
     if (check(h)) return 1;
     if (!h_target_offsets || !h_source_offsets) return fail("null offsets");
     cudaStream_t st = (cudaStream_t)stream;
-    const bool concurrent = !h->comm && !h->prof_on && latency_path(h, h_target_offsets, n_clouds) &&
-                            latency_path(h, h_source_offsets, n_clouds);
+    // Side by side while one side alone cannot fill the GPU: the single-block set-ups of small clouds, and up to ~1 M
+    // points per side (a 100k cloud's k-NN is one partial wave of blocks whose duration is its slowest chunk).  Each
+    // side has its own scratch (scr[0] / scr[1]).  Larger sides saturate the device on their own: sequential.
+    if (n_clouds <= 0) return fail("n_clouds must be positive");
+    const int64_t side_max = getenv("GICP_PAIR_OVERLAP_MAX") ? atoll(getenv("GICP_PAIR_OVERLAP_MAX")) : (1LL << 20);
+    const bool concurrent = !h->comm && !h->prof_on && h_target_offsets[n_clouds] <= side_max &&
+                            h_source_offsets[n_clouds] <= side_max;
     if (!concurrent) {
-        if (DISPATCH(h, set_cloud, h, GICP_TARGET, d_target, h_target_offsets, n_clouds, st)) return 1;
-        return DISPATCH(h, set_cloud, h, GICP_SOURCE, d_source, h_source_offsets, n_clouds, st);
+        if (DISPATCH(h, set_cloud, h, GICP_TARGET, d_target, h_target_offsets, n_clouds, st, 0)) return 1;
+        return DISPATCH(h, set_cloud, h, GICP_SOURCE, d_source, h_source_offsets, n_clouds, st, 0);
     }
     if (!h->side_stream) {
         CU(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
@@ -1009,8 +1027,8 @@ int gicpSetPair(gicpHandle h, const void* d_target, const int64_t* h_target_offs
     // join: `stream` continues only after the source side is set up
     CU(cudaEventRecord(h->ev_fork, st));
     CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
-    const int rc_t = DISPATCH(h, set_cloud, h, GICP_TARGET, d_target, h_target_offsets, n_clouds, st);
-    const int rc_s = rc_t ? 1 : DISPATCH(h, set_cloud, h, GICP_SOURCE, d_source, h_source_offsets, n_clouds, h->side_stream);
+    const int rc_t = DISPATCH(h, set_cloud, h, GICP_TARGET, d_target, h_target_offsets, n_clouds, st, 0);
+    const int rc_s = rc_t ? 1 : DISPATCH(h, set_cloud, h, GICP_SOURCE, d_source, h_source_offsets, n_clouds, h->side_stream, 1);
     CU(cudaEventRecord(h->ev_join, h->side_stream));
     CU(cudaStreamWaitEvent(st, h->ev_join, 0));
     h->last_stream = st;

@@ -82,10 +82,10 @@ int gicpSetParams(gicpHandle h, const gicpParams* p);
 int gicpSetTarget(gicpHandle h, const void* d_points, const int64_t* h_offsets, int32_t n_clouds, void* stream);
 int gicpSetSource(gicpHandle h, const void* d_points, const int64_t* h_offsets, int32_t n_clouds, void* stream);
 /* Both sides of a batch of pairs in one call (gicp.py:104 + :111 of one gicp() call).  Same result as gicpSetTarget
- * followed by gicpSetSource.  For small clouds (the reference's own workloads: every cloud <= 2048 points, <= 65536
- * points per side) the two sides are independent single-block builds, and the source side runs on an internal stream
- * concurrently with the target side; `stream` is forked before and joined after, so the caller still sees one
- * stream-ordered operation.                                                                                          */
+ * followed by gicpSetSource.  While one side alone cannot fill the device (up to 2^20 points per side: the reference's
+ * own scans, a 100k-point pair) the source side is set up on an internal stream, with its own scratch, concurrently
+ * with the target side; `stream` is forked before and joined after, so the caller still sees one stream-ordered
+ * operation.  Larger sides run one after the other.                                                                */
 int gicpSetPair(gicpHandle h, const void* d_target_points, const int64_t* h_target_offsets, const void* d_source_points,
                 const int64_t* h_source_offsets, int32_t n_clouds, void* stream);
 

@@ -79,8 +79,7 @@ if "3" in which and rank == 0:
     s_d, t_d = torch.as_tensor(src, device=dev), torch.as_tensor(tgt, device=dev)
 
     def run():
-        eng.set_target(t_d)
-        eng.set_source(s_d)
+        eng.set_pair(t_d, s_d)     # = set_target + set_source; the two set-ups overlap on the device
         return eng.register(history=False)
     dt, r = timed(run, 5)
     n_it = int(r.n_outer[0])

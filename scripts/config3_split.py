@@ -31,3 +31,14 @@ for name, fn in (("target", lambda: eng.set_target(t_d)), ("source", lambda: eng
     print(name, {k: round(v[0] / 3, 3) for k, v in p.items() if v[1]}, "launches per call", None)
 l0 = eng.launch_count; eng.set_target(t_d); l1 = eng.launch_count; eng.set_source(s_d); l2 = eng.launch_count
 print("launches target", l1 - l0, "source", l2 - l1)
+
+def run_pair():
+    eng.set_pair(t_d, s_d); return eng.register(history=False)
+for fn, name in ((run, "set_target + set_source + register"), (run_pair, "set_pair + register")):
+    for _ in range(3): fn()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(10): r = fn()
+    torch.cuda.synchronize()
+    print(f"{name}: {1e2 * (time.perf_counter() - t0):.3f} ms per pair, n_outer {int(r.n_outer[0])}")
+ra = run().T.clone(); rb = run_pair().T
+print("identical T:", bool(torch.equal(ra, rb)))

@@ -130,7 +130,7 @@ def test_small_3d_f32_both_paths(both_paths):
 def test_set_pair_equals_separate_calls():
     """gicpSetPair (both sides in one call; the two single-block set-ups run concurrently on the device) against
     gicpSetTarget + gicpSetSource: bit-identical grids, covariances and registration, repeated so that a race between
-    the two internal streams would show; a large pair takes the sequential branch of the same call."""
+    the two internal streams would show; larger pairs (multi-kernel set-up) side by side and one after the other."""
     import torch
     from generalized_icp_b200 import synthetic
     from generalized_icp_b200.engine import GicpEngine
@@ -165,12 +165,28 @@ def test_set_pair_equals_separate_calls():
     for side in (0, 1):
         assert torch.equal(eng_a.covariances(side), eng_b.covariances(side))
     assert torch.equal(eng_a.register(history=False).T, eng_b.register(history=False).T)
-    # large clouds: the same entry point, sequential branch
+    # larger clouds (multi-kernel grid build, sort scratch per side): side by side, and the sequential branch of the
+    # same entry point (GICP_PAIR_OVERLAP_MAX=0)
     s3, t3, _ = synthetic.patches3d_pair(n=20000, n_patches=8, cube=40.0, patch=30.0, seed=4)
     e3a, e3b = GicpEngine(3, "f32"), GicpEngine(3, "f32")
     for e in (e3a, e3b):
         e.set_params(k=20, max_distance_nearest_neighbors=5.0, max_distance_correspondence=2.0)
     s3 = torch.as_tensor(s3, dtype=torch.float32, device="cuda"); t3 = torch.as_tensor(t3, dtype=torch.float32, device="cuda")
     e3a.set_target(t3); e3a.set_source(s3)
-    e3b.set_pair(t3, s3)
-    assert torch.equal(e3a.register(history=False).T, e3b.register(history=False).T)
+    Ta = e3a.register(history=False).T
+    for rep in range(3):
+        e3b.set_pair(t3, s3)
+        for side in (0, 1):
+            assert torch.equal(e3a.covariances(side), e3b.covariances(side))
+            assert torch.equal(e3a.knn(side)[0], e3b.knn(side)[0])
+        assert torch.equal(Ta, e3b.register(history=False).T)
+    saved = os.environ.get("GICP_PAIR_OVERLAP_MAX")
+    os.environ["GICP_PAIR_OVERLAP_MAX"] = "0"
+    try:
+        e3b.set_pair(t3, s3)
+        assert torch.equal(Ta, e3b.register(history=False).T)
+    finally:
+        if saved is None:
+            os.environ.pop("GICP_PAIR_OVERLAP_MAX", None)
+        else:
+            os.environ["GICP_PAIR_OVERLAP_MAX"] = saved
