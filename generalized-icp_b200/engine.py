@@ -211,6 +211,46 @@ class GicpEngine:
                     src_cov0=hd[offs[3]:offs[4]].reshape(n_s, d, d), tgt_cov=hd[offs[4]:offs[5]].reshape(n_t, d, d),
                     n_outer=n_outer, converged_at=conv, inliers=hi[2:2 + mi][:n_outer])
 
+    def register_next_scan_host(self, scan, have_previous):
+        """Scan sequences with HOST scans (robot-visualization.py:246-252): the previous target is promoted to the
+        source (grids + covariances reused), `scan` becomes the target, the pair is registered.  One staged upload, one
+        read-back (T, n_outer, converged_at), no per-call allocations; the first scan of a sequence
+        (`have_previous=False`) is only set up.  Returns None or dict(T, n_outer, converged_at)."""
+        d, d1 = self.dim, self.dim + 1
+        np_dt = np.float64 if self.storage == "f64" else np.float32
+        scan = np.ascontiguousarray(scan, dtype=np_dt)
+        if scan.ndim != 2 or scan.shape[1] != d:
+            raise ValueError(f"expected (N, {d}) points, got {scan.shape}")
+        n = scan.shape[0]
+        if getattr(self, "_sc_rows", -1) < n:
+            cap = max(n, 1024)
+            # two slots: the promoted source still refers to the previous scan's device array
+            self._sc_host = [torch.empty((cap, d), dtype=self.dtype, pin_memory=True) for _ in range(2)]
+            self._sc_dev = [torch.empty((cap, d), dtype=self.dtype, device=self.device) for _ in range(2)]
+            self._sc_out_dev = torch.empty((d1 * d1 + 1,), dtype=torch.float64, device=self.device)
+            self._sc_out_host = torch.empty((d1 * d1 + 1,), dtype=torch.float64, pin_memory=True)
+            self._sc_rows, self._sc_slot = cap, 0
+        slot = self._sc_slot = self._sc_slot ^ 1
+        self._sc_host[slot].numpy()[:n] = scan
+        self._sc_dev[slot][:n].copy_(self._sc_host[slot][:n], non_blocking=True)
+        vp = C.c_void_p
+        st = self._stream()
+        if have_previous:
+            self.promote_target_to_source()
+        self._keep[TARGET] = self._sc_dev[slot]
+        self._n[TARGET] = (n, 1)
+        _lib.check(self.lib.gicpSetTarget(self._h, vp(self._sc_dev[slot].data_ptr()), (C.c_int64 * 2)(0, n), 1, st))
+        if not have_previous:
+            return None
+        dp = self._sc_out_dev.data_ptr()
+        ip = dp + 8 * d1 * d1
+        _lib.check(self.lib.gicpRegister(self._h, None, vp(dp), vp(ip), vp(ip + 4), None, None, None, st))
+        self._sc_out_host.copy_(self._sc_out_dev, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        hd = self._sc_out_host.numpy().copy()
+        hi = hd[d1 * d1:].view(np.int32)
+        return dict(T=hd[:d1 * d1].reshape(d1, d1), n_outer=int(hi[0]), converged_at=int(hi[1]))
+
     def register_host_batch(self, h_src, h_tgt, offsets, chunk_pairs=1024, history=False):
         """Batches that live in (pinned) HOST memory: pairs are registered in chunks, and the host->device
         copy of chunk i+1 runs on a second stream while chunk i is being registered, so the PCIe transfer

@@ -29,8 +29,6 @@ class ScanOdometry:
 
     def __init__(self, start_pose=(50.0, 400.0, 0.0), storage="f64", **params):
         from .engine import GicpEngine
-        import torch
-        self._torch = torch
         self.eng = GicpEngine(2, storage)
         p = dict(max_distance_nearest_neighbors=200.0, tolerance=1.0)   # robot-visualization.py:160-161
         p.update(params)
@@ -42,20 +40,13 @@ class ScanOdometry:
         self._have = False
 
     def push(self, scan):
-        torch = self._torch
-        pts = torch.as_tensor(np.ascontiguousarray(np.asarray(scan, dtype=np.float64)), device=self.eng.device)
-        if self.eng.dtype != torch.float64:
-            pts = pts.to(self.eng.dtype)
-        if self._have:
-            self.eng.promote_target_to_source()     # previous scan: grids + covariances reused
-        self.eng.set_target(pts)
+        r = self.eng.register_next_scan_host(np.asarray(scan, dtype=np.float64), self._have)
         if not self._have:
             self._have = True
             return None
-        r = self.eng.register(history=False)
-        T = r.T[0].cpu().numpy()
+        T = r["T"]
         self.transforms.append(T)
-        self.iterations.append(int(r.n_outer[0]))
+        self.iterations.append(r["n_outer"])
         self.pose = integrate_pose(self.pose, T)
         self.poses.append(self.pose)
         return T
