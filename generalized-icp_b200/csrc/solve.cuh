@@ -266,16 +266,44 @@ __device__ void inner_solve_warp(SolveScratch<D>& sc, const double* G, double c0
             for (int x = 0; x < NPAR; ++x) gmax = fmax(gmax, fabs(sc.g[x]));
             bool go = gmax > 1e-11 * fmax(1.0, fabs(f));
             if (go) {
+                // Second-order term the Gauss-Newton matrix 2 J^T H J misses: Z is linear in dt, and for the left
+                // perturbation dR <- exp([eta]x) dR,  d2 dR / d eta_k d eta_l = (E_k E_l + E_l E_k) dR / 2  with
+                // E_k E_l = e_l e_k^T - delta_kl I, so  Gam . d2Z = (P_kl + P_lk) / 2 - delta_kl tr P,  P = dR Gam_R^T
+                // (Gam_R: the rotation columns of the gradient wrt Z).  With it the iteration is Newton's (quadratic
+                // instead of linear convergence to the same minimiser); it is dropped for an iteration whose matrix it
+                // makes indefinite.
+                double Cn[3][3] = {};
+                bool newton = false;
+                if constexpr (D == 3) {
+                    double P[3][3], trP = 0.0;
+                    for (int k = 0; k < 3; ++k)
+                        for (int l = 0; l < 3; ++l) {
+                            double v = 0.0;
+                            for (int j = 0; j < 3; ++j) v += sc.dR[k][j] * sc.Gam[l * NP + 1 + j];
+                            P[k][l] = v;
+                        }
+                    trP = P[0][0] + P[1][1] + P[2][2];
+                    for (int k = 0; k < 3; ++k)
+                        for (int l = 0; l < 3; ++l) Cn[k][l] = 0.5 * (P[k][l] + P[l][k]) - (k == l ? trP : 0.0);
+                    newton = true;
+                }
                 bool accepted = false;
                 double stepmax = 0.0;
                 for (int tries = 0; tries < 40; ++tries) {
                     double L[NPAR][NPAR], step[NPAR];
                     for (int x = 0; x < NPAR; ++x) {
-                        for (int y = 0; y < NPAR; ++y) L[x][y] = sc.A[x][y];
+                        for (int y = 0; y < NPAR; ++y) {
+                            L[x][y] = sc.A[x][y];
+                            if (newton && x >= D && y >= D) L[x][y] += Cn[x - D][y - D];
+                        }
                         L[x][x] += lam * sc.A[x][x];
                         step[x] = -sc.g[x];
                     }
-                    if (!spd_solve<NPAR>(L, step)) { lam = fmax(lam * 10.0, 1e-6); continue; }
+                    if (!spd_solve<NPAR>(L, step)) {
+                        if (newton) { newton = false; continue; }
+                        lam = fmax(lam * 10.0, 1e-6);
+                        continue;
+                    }
                     double dRn[D][D], dtn[D], thn;
                     compose_rotation<D>(step + D, sc.dR, sc.dtheta, dRn, &thn);
                     for (int c_ = 0; c_ < D; ++c_) {

@@ -1,5 +1,11 @@
-import sys, time
-sys.path.insert(0, "/root/repo")
+"""Where one 100k + 100k pair (BASELINE configs[2]) spends its time: wall split with synchronisations, per-stage device
+times, per-side k-NN, and gicpSetPair (set-ups side by side) against the two separate calls.
+    python scripts/config3_split.py"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
 from generalized_icp_b200 import synthetic
 from generalized_icp_b200.engine import GicpEngine
@@ -31,6 +37,9 @@ for name, fn in (("target", lambda: eng.set_target(t_d)), ("source", lambda: eng
     print(name, {k: round(v[0] / 3, 3) for k, v in p.items() if v[1]}, "launches per call", None)
 l0 = eng.launch_count; eng.set_target(t_d); l1 = eng.launch_count; eng.set_source(s_d); l2 = eng.launch_count
 print("launches target", l1 - l0, "source", l2 - l1)
+
+eng.profile(False)   # per-stage timing forces the sequential branch of gicpSetPair
+
 
 def run_pair():
     eng.set_pair(t_d, s_d); return eng.register(history=False)
