@@ -14,7 +14,7 @@ namespace gicp {
 
 // entry e of the dense form Hd[c * NP + a][d * NP + b] = H(a, b, c, d) of the packed reduced Hessian Hq [NAB][NS]
 // (K3b's layout): the solver applies H 5-8 times per LM iteration, as dense matrix-vector products
-template <int D> __device__ __forceinline__ double dense_H_entry(const double* Hq, int e) {
+template <int D> __host__ __device__ __forceinline__ double dense_H_entry(const double* Hq, int e) {
     using DD = Dim<D>;
     constexpr int DN = D * DD::NP;
     const int row = e / DN, col = e % DN;
@@ -38,7 +38,7 @@ template <int D> struct SolveScratch {
 // on it); returns false when A is not positive definite (same pivots as a Cholesky factorisation).  No square roots and
 // one reciprocal per pivot: in float64 a division or a square root is a ~20-instruction dependent chain, and the damped
 // solve sits on the critical path of every LM iteration of a small registration (one lane, everybody else waits).
-template <int N> __device__ inline bool spd_solve(double A[N][N], double b[N]) {
+template <int N> __host__ __device__ inline bool spd_solve(double A[N][N], double b[N]) {
     double inv[N];
     for (int j = 0; j < N; ++j) {
         double d = A[j][j];
@@ -99,6 +99,8 @@ __device__ inline void compose_rotation(const double* step_rot, const double dR[
     }
 }
 
+// (spd_solve, dense_H_entry and inner_solve_2d are __host__ __device__: tests/test_host.py compiles them for the host
+// and checks the minimiser on the reference's own inner problems without a GPU.)
 // 2-D, ONE LANE: Levenberg-Marquardt on the reduced form  f(Z) = c - 2<G,Z> + <Z, H Z>,  Z = [dt | dR - I]  (the same
 // iteration as the warp-cooperative 3-D version below: same damping, acceptance and stop rules), evaluated on the
 // projection of the form onto the four numbers Z depends on.  With dR = rot(th):
@@ -109,7 +111,7 @@ __device__ inline void compose_rotation(const double* step_rot, const double dR[
 // 2/3 of the time of a small registration - every other warp of the fused loop waits for this lane.  The
 // warp-cooperative formulation was measured slower than one lane in 2-D: its hand-overs cost more than 3 parameters
 // can save.)
-__device__ inline void inner_solve_2d(const double* Hq, const double* G, double c0, int max_it, double dR[2][2],
+__host__ __device__ inline void inner_solve_2d(const double* Hq, const double* G, double c0, int max_it, double dR[2][2],
                                       double dt[2], double* dtheta, double* fmin) {
     auto Hd = [&](int e, int f) { return dense_H_entry<2>(Hq, e * 6 + f); };
     const double M00 = Hd(0, 0), M01 = Hd(0, 3), M02 = Hd(0, 1) + Hd(0, 5), M03 = Hd(0, 4) - Hd(0, 2);

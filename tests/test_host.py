@@ -127,3 +127,75 @@ def test_reduced_form_reproduces_loss_and_grad_loss(name, golden):
             gw = g[gk][k]
             gg = reduced_form_grad2d(red, T, x)
             assert np.abs(gg - gw).max() <= 1e-8 * max(1.0, np.abs(gw).max()), (k, xk, gg, gw)
+
+
+@pytest.fixture(scope="module")
+def solve_host(tmp_path_factory):
+    """tests/host_harness/solve_host.cu: the 2-D inner solver and the damped linear solve of csrc/solve.cuh
+    (__host__ __device__ functions) compiled for the host with nvcc - product source, run here as the thing under test."""
+    import ctypes
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    out = str(tmp_path_factory.mktemp("solve_host") / "solve_host.so")
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_harness", "solve_host.cu")
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O2", "-Xcompiler", "-fPIC",
+                    "-shared", "-o", out, src], check=True)
+    lib = ctypes.CDLL(out)
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.gicp_test_solve2d.argtypes = [dp, ctypes.c_int, dp]
+    lib.gicp_test_spd_solve6.argtypes = [dp, dp]
+    return lib
+
+
+@pytest.mark.parametrize("name", ["config1_seed0", "config1_seed3", "config2_rays90_pair0", "config2_rays360_pair2"])
+def test_inner_solver_minimises_the_references_inner_problems(name, golden, solve_host):
+    """K4's 2-D solver (csrc/solve.cuh inner_solve_2d, compiled for the host) on the reference's own inner problems
+    (gicp.py:148-152: matches and weights of every outer iteration of a recorded run): the point it returns is a
+    stationary point of the frozen objective (grad_loss of gicp.py:60-76 vanishes there), its value is the reduced
+    form's value at that point, and it is at least as good as what the reference's fmin_cg reached."""
+    import ctypes
+    from generalized_icp_b200.engine import reduced_form_grad2d, reduced_form_loss
+    g = golden(name)
+    mu = 0.5 * (g["tgt"].min(0) + g["tgt"].max(0))
+    dp = ctypes.POINTER(ctypes.c_double)
+    n_it = len(g["it_fopt"])
+    for k in sorted(set(range(min(n_it, 8))) | {n_it - 1}):     # the first outer iterations and the last one
+        T = g["all_T"][k]
+        red = np.ascontiguousarray(_reduced_form_numpy(g["src"], g["it_q"][k], g["it_W"][k], T, mu))
+        out = np.zeros(8)
+        assert solve_host.gicp_test_solve2d(red.ctypes.data_as(dp), 50, out.ctypes.data_as(dp)) == 0
+        dtc, dth, fmin, dR = out[:2], out[2], out[3], out[4:].reshape(2, 2)
+        assert np.allclose(dR, [[np.cos(dth), -np.sin(dth)], [np.sin(dth), np.cos(dth)]], atol=1e-15)
+        # un-centre and compose exactly as solve_pair does: dt = dt_c - (dR - I) mu,  T_new = [dR R | dR t + dt]
+        dt = dtc - (dR - np.eye(2)) @ mu
+        Tn = np.eye(3)
+        Tn[:2, :2] = dR @ T[:2, :2]
+        Tn[:2, 2] = dR @ T[:2, 2] + dt
+        x_new = np.array([Tn[0, 2], Tn[1, 2], np.arctan2(Tn[1, 0], Tn[0, 0])])
+        f_at = reduced_form_loss(red, 2, T, Tn)
+        assert abs(f_at - fmin) <= 1e-9 * max(1.0, abs(fmin))
+        grad = reduced_form_grad2d(red, T, x_new)
+        scale = max(1.0, np.abs(reduced_form_grad2d(red, T, g["it_x0"][k])).max())
+        assert np.abs(grad).max() <= 1e-8 * scale, (k, grad, scale)
+        assert fmin <= float(g["it_loss_at_xopt"][k]) + 1e-9 * max(1.0, abs(fmin)), (k, fmin, g["it_loss_at_xopt"][k])
+
+
+def test_damped_solve_host(solve_host):
+    """spd_solve<6> (LDL^T, csrc/solve.cuh) against numpy on random SPD systems; an indefinite matrix is reported."""
+    import ctypes
+    dp = ctypes.POINTER(ctypes.c_double)
+    rng = np.random.default_rng(7)
+    for _ in range(50):
+        B = rng.normal(size=(6, 6))
+        A = np.ascontiguousarray(B @ B.T + 1e-3 * np.eye(6))
+        b = rng.normal(size=6)
+        x = b.copy()
+        assert solve_host.gicp_test_spd_solve6(A.ctypes.data_as(dp), x.ctypes.data_as(dp)) == 0
+        want = np.linalg.solve(A, b)
+        assert np.abs(x - want).max() <= 1e-9 * max(1.0, np.abs(want).max())
+    A = np.ascontiguousarray(np.diag([1.0, 2.0, -1.0, 1.0, 1.0, 1.0]))
+    x = np.ones(6)
+    assert solve_host.gicp_test_spd_solve6(A.ctypes.data_as(dp), x.ctypes.data_as(dp)) == 1
