@@ -158,7 +158,7 @@ template <typename T> __device__ __forceinline__ T warp_sum(T v) {
 // Unit eigenvector of the smallest eigenvalue of the symmetric 3x3 matrix
 // [a00 a01 a02; . a11 a12; . . a22].  Degenerate (isotropic) input -> (1,0,0), which is
 // what LAPACK's eigh returns for a multiple of the identity.
-__device__ inline void smallest_eigvec3(double a00, double a01, double a02, double a11, double a12, double a22,
+__host__ __device__ inline void smallest_eigvec3(double a00, double a01, double a02, double a11, double a12, double a22,
                                         double n[3]) {
     const double scale = fmax(fmax(fabs(a00), fabs(a11)), fmax(fabs(a22), fmax(fabs(a01), fmax(fabs(a02), fabs(a12)))));
     n[0] = 1.0; n[1] = 0.0; n[2] = 0.0;

@@ -68,7 +68,7 @@ __device__ __forceinline__ bool key_less(double d, int i, double dd, int ii) {
 // gicp.py:11-16 / SURVEY 8c: regularised covariance from the neighbourhood's scatter matrix
 // S (00 01 02 11 12 22, already divided by cnt-1).  C: D(D+1)/2 entries.
 template <int D>
-__device__ __forceinline__ void regularised_cov(const double S[6], bool ident, double lam_t, double lam_n, double* C) {
+__host__ __device__ __forceinline__ void regularised_cov(const double S[6], bool ident, double lam_t, double lam_n, double* C) {
     bool finite = true;
 #pragma unroll
     for (int i = 0; i < 6; ++i) finite = finite && isfinite(S[i]);

@@ -131,22 +131,29 @@ def test_reduced_form_reproduces_loss_and_grad_loss(name, golden):
 
 @pytest.fixture(scope="module")
 def solve_host(tmp_path_factory):
-    """tests/host_harness/solve_host.cu: the 2-D inner solver and the damped linear solve of csrc/solve.cuh
-    (__host__ __device__ functions) compiled for the host with nvcc - product source, run here as the thing under test."""
+    """tests/host_harness/*.cu: the 2-D inner solver and the damped linear solve of csrc/solve.cuh and the covariance
+    tail of csrc/knn_cov.cuh (__host__ __device__ functions) compiled for the host with nvcc - product source, run here
+    as the thing under test."""
     import ctypes
     import shutil
     import subprocess
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
-    out = str(tmp_path_factory.mktemp("solve_host") / "solve_host.so")
-    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_harness", "solve_host.cu")
-    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O2", "-Xcompiler", "-fPIC",
-                    "-shared", "-o", out, src], check=True)
-    lib = ctypes.CDLL(out)
+    tmp = tmp_path_factory.mktemp("host_harness")
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_harness")
+    libs = []
+    for name in ("solve_host", "cov_host"):
+        out = str(tmp / (name + ".so"))
+        subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O2", "-Xcompiler", "-fPIC",
+                        "-shared", "-o", out, os.path.join(here, name + ".cu")], check=True)
+        libs.append(ctypes.CDLL(out))
+    lib, cov = libs
     dp = ctypes.POINTER(ctypes.c_double)
     lib.gicp_test_solve2d.argtypes = [dp, ctypes.c_int, dp]
     lib.gicp_test_spd_solve6.argtypes = [dp, dp]
+    cov.gicp_test_regularised_cov.argtypes = [ctypes.c_int, dp, ctypes.c_double, ctypes.c_double, dp]
+    lib.regularised_cov = cov.gicp_test_regularised_cov
     return lib
 
 
@@ -199,3 +206,53 @@ def test_damped_solve_host(solve_host):
     A = np.ascontiguousarray(np.diag([1.0, 2.0, -1.0, 1.0, 1.0, 1.0]))
     x = np.ones(6)
     assert solve_host.gicp_test_spd_solve6(A.ctypes.data_as(dp), x.ctypes.data_as(dp)) == 1
+
+
+def test_covariance_tail_host(solve_host):
+    """K2's covariance tail (closed-form symmetric eigen-solve + regularisation, csrc/knn_cov.cuh regularised_cov,
+    compiled for the host) against numpy's eigh on the formula of gicp.py:11-16 / the oracle's
+    covariances_from_neighbors: generic, nearly planar, nearly collinear and badly scaled scatter matrices; non-finite
+    input gives the identity (gicp.py:31-32)."""
+    import ctypes
+    dp = ctypes.POINTER(ctypes.c_double)
+    rng = np.random.default_rng(11)
+    lam_t, lam_n = 100.0, 10.0
+
+    def want(S, dim):
+        evals, evecs = np.linalg.eigh(S)
+        if dim == 2:
+            v = evecs[:, 1]
+            return lam_n * np.eye(2) + (lam_t - lam_n) * np.outer(v, v)
+        n = evecs[:, 0]
+        return lam_t * np.eye(3) - (lam_t - lam_n) * np.outer(n, n)
+
+    def got(S, dim):
+        S6 = np.zeros(6)
+        if dim == 2:
+            S6[0], S6[1], S6[3] = S[0, 0], S[0, 1], S[1, 1]
+        else:
+            S6[:] = [S[0, 0], S[0, 1], S[0, 2], S[1, 1], S[1, 2], S[2, 2]]
+        C = np.zeros(6)
+        solve_host.regularised_cov(dim, S6.ctypes.data_as(dp), lam_t, lam_n, C.ctypes.data_as(dp))
+        if dim == 2:
+            return np.array([[C[0], C[1]], [C[1], C[2]]])
+        return np.array([[C[0], C[1], C[2]], [C[1], C[3], C[4]], [C[2], C[4], C[5]]])
+
+    for dim in (2, 3):
+        for case in range(200):
+            Q, _ = np.linalg.qr(rng.normal(size=(dim, dim)))
+            ev = np.sort(rng.uniform(0.1, 1.0, dim))
+            if case % 4 == 1:
+                ev[0] = ev[-1] * 1e-6            # nearly planar (3-D) / nearly collinear (2-D)
+            if case % 4 == 2 and dim == 3:
+                ev[1] = ev[0] * (1 + 1e-3)       # two close small eigenvalues, one dominant direction
+                ev[0] *= 1e-2
+                ev[1] *= 1e-2
+            scale = 10.0 ** rng.integers(-6, 7) if case % 4 == 3 else 1.0
+            S = (Q * ev) @ Q.T * scale
+            S = 0.5 * (S + S.T)
+            gap = (ev[-1] - ev[-2]) if dim == 2 else (ev[1] - ev[0])
+            tol = 1e-9 * (lam_t - lam_n) / max(gap / ev[-1], 1e-12) * 10
+            assert np.abs(got(S, dim) - want(S, dim)).max() <= max(tol, 1e-9), (dim, case, ev)
+        bad = np.full((dim, dim), np.nan)
+        assert np.array_equal(got(bad, dim), np.eye(dim))
